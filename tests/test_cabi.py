@@ -1,0 +1,88 @@
+"""
+CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol include/tnmf_b200.h
+declares, and its argument validation / shape logic (no kernel launches) follows the reference's conventions.
+"""
+import ctypes
+import os
+import re
+
+import pytest
+
+from tnmf_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    _lib.build()
+    return _lib.load()
+
+
+def test_header_and_binding_agree(lib):
+    header = open(os.path.join(ROOT, 'include', 'tnmf_b200.h')).read()
+    declared = set(re.findall(r'\b(tnmf_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.tnmf_abi_version() == int(re.search(r'#define TNMF_ABI_VERSION (\d+)', header).group(1))
+
+
+def test_struct_layout_matches_header():
+    # 8 int32 + 2*3 int32 + 2 int64 = 72 bytes, no padding surprises
+    assert ctypes.sizeof(_lib.Problem) == 8 * 4 + 6 * 4 + 2 * 8
+    assert _lib.Problem.h_stride_n.offset == 56
+
+
+@pytest.mark.parametrize('mode,expected', [('valid', (24, 18)), ('full', (16, 16)), ('circular', (20, 17))])
+def test_transform_shape_follows_reference(lib, mode, expected):
+    """tnmf/backends/_Backend.py:60-73."""
+    p = _lib.make_problem(3, 2, 4, (20, 17), (5, 2), _lib.TNMF_F64, mode)
+    t = (ctypes.c_int32 * 3)()
+    assert lib.tnmf_transform_shape(ctypes.byref(p), t) == 0
+    assert (t[0], t[1]) == expected
+
+
+def test_argument_validation(lib):
+    p = _lib.make_problem(3, 2, 4, (20,), (5,), _lib.TNMF_F32)
+    assert lib.tnmf_reconstruct(ctypes.byref(p), None, None, None, None) == _lib.TNMF_EINVAL
+    assert lib.tnmf_workspace_bytes(ctypes.byref(p)) % 256 == 0 and lib.tnmf_workspace_bytes(ctypes.byref(p)) > 0
+    p.mode = 7
+    assert lib.tnmf_workspace_bytes(ctypes.byref(p)) == 0
+    bad = _lib.make_problem(3, 2, 4, (4,), (5,), _lib.TNMF_F32, 'full')           # atom larger than sample
+    t = (ctypes.c_int32 * 3)()
+    assert lib.tnmf_transform_shape(ctypes.byref(bad), t) == _lib.TNMF_EINVAL
+    with pytest.raises(ValueError):
+        _lib.make_problem(1, 1, 1, (4,), (2,), 0, 'reflect')
+    with pytest.raises(NotImplementedError):
+        _lib.make_problem(1, 1, 1, (4, 4, 4, 4), (2, 2, 2, 2), 0)
+
+
+def test_status_translation(lib):
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.TNMF_EUNSUPPORTED)
+    with pytest.raises(ValueError):
+        _lib.check(_lib.TNMF_EINVAL)
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.TNMF_ECUDA + 2)
+    _lib.check(0)
+
+
+def test_tiled_path_selection(lib):
+    f32_2d = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32)
+    f64_2d = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F64)
+    f32_3d = _lib.make_problem(2, 1, 2, (8, 8, 8), (3, 3, 3), _lib.TNMF_F32)
+    assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_2d)) == 1
+    assert lib.tnmf_uses_tiled_path(ctypes.byref(f64_2d)) == 0
+    assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_3d)) == 0
+    f32_2d.path = _lib.PATHS['generic']
+    assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_2d)) == 0
+
+
+def test_backend_refuses_to_run_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from tnmf_b200 import B200_Backend
+    with pytest.raises(RuntimeError):
+        B200_Backend()

@@ -1,0 +1,380 @@
+"""
+GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C-ABI
+(tnmf_b200._lib -> libtnmf_b200.so), against
+  * the golden fixtures generated from the unmodified reference (tests/golden/make_golden.py), and
+  * the CPU oracle (oracle/tnmf_oracle.py) on the same seeded inputs.
+
+Tolerances (stated per test):
+  float64  : the kernels and the reference differ by summation order only -> rtol 1e-9 .. 1e-10
+  float32  : energy trajectory within 1e-4 relative, W/H within 1e-3 of max|ref| after 100 iterations
+             (BASELINE.json north_star; SURVEY 7 "bit-level order of operations" explains why elementwise
+             relative error on H is meaningless), single operations within 2e-5 of max|ref|.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import tnmf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+MODES = ('valid', 'full', 'circular')
+REFERENCE_TEST_1D_ENERGIES = {'valid': 2.34946, 'full': 1.87180, 'circular': 3.13228}   # tnmf/tests/test_1d.py:17-22
+
+
+def _backend(V, W, H, mode='valid', path='auto'):
+    from tnmf_b200 import B200_Backend
+    be = B200_Backend(reconstruction_mode=mode, kernel_path=path)
+    state = np.random.get_state()
+    Wd, Hd = be.initialize(V, W.shape[2:], W.shape[0], None, tuple(range(-(W.ndim - 2), 0)))
+    np.random.set_state(state)
+    Wd.copy_(torch.from_numpy(W))
+    Hd.copy_(torch.from_numpy(H))
+    return be, Wd, Hd
+
+
+def _close(a, b, tol):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    scale = max(float(np.abs(b).max()), 1e-30)
+    err = float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max()) / scale
+    assert err <= tol, f'max|delta|/max|ref| = {err:.3e} > {tol:.1e}'
+
+
+def _paths(dtype, ndim):
+    if dtype == np.float32 and ndim <= 2:
+        return ('generic', 'tiled')
+    return ('generic',)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# single operations against the reference's outputs (all modes, 1-D / 2-D / 3-D)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('case', ['d1', 'd2', 'd3'])
+def test_single_operations_vs_reference(case, mode, dtype, golden):
+    g = golden('ref_ops')
+    k = f'{case}_{mode}_'
+    V, W, H = (g[k + n].astype(dtype) for n in 'VWH')
+    tol = 1e-10 if dtype == np.float64 else 2e-5
+    for path in _paths(dtype, V.ndim - 2):
+        be, Wd, Hd = _backend(V, W, H, mode, path)
+        assert tuple(Hd.shape[2:]) == orc.transform_shape(mode, V.shape[2:], W.shape[2:])
+        _close(be.reconstruct(Wd, Hd), g[k + 'R'], tol)
+        neg, pos = be.reconstruction_gradient_H(V, Wd, Hd)
+        _close(neg, g[k + 'negH'], tol)
+        _close(pos, g[k + 'posH'], tol)
+        neg, pos = be.reconstruction_gradient_W(V, Wd, Hd)
+        _close(neg, g[k + 'negW'], tol)
+        _close(pos, g[k + 'posW'], tol)
+        e = be.reconstruction_energy(V, Wd, Hd)
+        assert np.isclose(e, g[k + 'E'], rtol=1e-10 if dtype == np.float64 else 1e-5)
+        # partial reconstruction: strided single-atom view of H (tnmf/backends/_Backend.py:124-125)
+        _close(be.partial_reconstruct(Wd, Hd, 1), orc.reconstruct(W[1:2].astype(np.float64),
+                                                                  H[:, 1:2].astype(np.float64), mode), tol)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the reference's own known-answer test (tnmf/tests/test_1d.py)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fused', [True, False])
+@pytest.mark.parametrize('mode', MODES)
+def test_known_answer_test_1d(mode, fused, golden):
+    from tnmf_b200 import TransformInvariantNMF
+    g = golden('ref_test_1d')
+    np.random.seed(42)
+    nmf = TransformInvariantNMF(n_atoms=3, atom_shape=(5,), reconstruction_mode=mode, fused=fused)
+    nmf.fit(g['V'], inhibition_strength=0.1, n_iterations=10)
+    assert np.isclose(nmf._energy_function(), REFERENCE_TEST_1D_ENERGIES[mode])      # the reference's assertion
+    assert np.isclose(nmf._energy_function(), g[f'E_{mode}'], rtol=1e-10)
+    assert np.allclose(nmf.W, g[f'W_{mode}'], rtol=1e-9, atol=1e-12)
+    assert np.allclose(nmf.H, g[f'H_{mode}'], rtol=1e-9, atol=1e-12)
+    assert np.allclose(nmf.R, g[f'R_{mode}'], rtol=1e-9, atol=1e-12)
+    assert np.allclose(nmf.W.sum(axis=-1), 1.0)                                     # tnmf/tests/test_1d.py:90-91
+
+
+# ---------------------------------------------------------------------------------------------------------
+# batch fits in 2-D with sparsity / inhibition / cross-atom inhibition, all modes, float64
+# ---------------------------------------------------------------------------------------------------------
+VARIANTS = {
+    'plain': dict(),
+    'sparse': dict(sparsity_H=0.1),
+    'inhib': dict(inhibition_strength=0.5),
+    'cross': dict(cross_atom_inhibition_strength=0.3, sparsity_H=0.05),
+    'all': dict(sparsity_H=0.1, inhibition_strength=0.2, cross_atom_inhibition_strength=0.4),
+}
+
+
+@pytest.mark.parametrize('fused', [True, False])
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('variant', list(VARIANTS))
+def test_batch_fit_2d(mode, variant, fused, golden):
+    from tnmf_b200 import TransformInvariantNMF
+    g = golden('ref_fit_2d')
+    np.random.seed(5)
+    nmf = TransformInvariantNMF(n_atoms=4, atom_shape=(5, 3), reconstruction_mode=mode, fused=fused)
+    traj = []
+    nmf.fit(g['V'], n_iterations=20, progress_callback=lambda m, i: traj.append(m._energy_function()) or True,
+            **VARIANTS[variant])
+    k = f'{mode}_{variant}_'
+    assert np.allclose(traj, g[k + 'E'], rtol=1e-9)
+    assert np.allclose(nmf.W, g[k + 'W'], rtol=1e-8, atol=1e-12)
+    assert np.allclose(nmf.H, g[k + 'H'], rtol=1e-8, atol=1e-12)
+
+
+def test_batch_fit_custom_inhibition_range(golden):
+    from tnmf_b200 import TransformInvariantNMF
+    g = golden('ref_fit_2d')
+    np.random.seed(5)
+    nmf = TransformInvariantNMF(n_atoms=4, atom_shape=(5, 3), inhibition_range=(2, 1))
+    nmf.fit(g['V'], n_iterations=20, inhibition_strength=0.7)
+    assert np.isclose(nmf._energy_function(), g['valid_range_E'][-1], rtol=1e-9)
+    assert np.allclose(nmf.W, g['valid_range_W'], rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize('path', ['generic', 'tiled'])
+def test_batch_fit_float32_100_iterations(path, golden):
+    """north_star tolerance: energy trajectory within 1e-4 relative, W/H within 1e-3 max-relative after 100
+    iterations, against the reference numpy backend run in float32."""
+    from tnmf_b200 import TransformInvariantNMF
+    g = golden('ref_fit_2d')
+    V32 = g['V'].astype(np.float32)
+    np.random.seed(5)
+    nmf = TransformInvariantNMF(n_atoms=4, atom_shape=(5, 3), kernel_path=path)
+    traj = []
+    nmf.fit(V32, n_iterations=100, sparsity_H=0.1,
+            progress_callback=lambda m, i: traj.append(m._energy_function()) or True)
+    assert nmf.W.dtype == np.float32 and nmf.H.dtype == np.float32
+    assert np.allclose(traj, g['f32_E'], rtol=1e-4)
+    assert np.abs(nmf.W - g['f32_W']).max() <= 1e-3 * np.abs(g['f32_W']).max()
+    assert np.abs(nmf.H - g['f32_H']).max() <= 1e-3 * np.abs(g['f32_H']).max()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# minibatch schedules and streams
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('fused', [True, False])
+@pytest.mark.parametrize('alg', ['Cyclic_MU', 'ASG_MU', 'GSG_MU', 'ASAG_MU', 'GSAG_MU'])
+def test_minibatch_schedules(alg, fused, golden):
+    from tnmf_b200 import MiniBatchAlgorithm, TransformInvariantNMF
+    g = golden('ref_minibatch')
+    np.random.seed(42)
+    nmf = TransformInvariantNMF(n_atoms=3, atom_shape=(4, 4), fused=fused)
+    nmf.fit_minibatches(g['V'], sparsity_H=0.1, algorithm=MiniBatchAlgorithm[alg], batch_size=3, n_epochs=5,
+                        sag_lambda=0.8, progress_callback=lambda *_: True)
+    assert np.isclose(nmf._energy_function(), g[f'{alg}_E'], rtol=1e-9)
+    assert np.allclose(nmf.W, g[f'{alg}_W'], rtol=1e-8, atol=1e-12)
+    assert np.allclose(nmf.H, g[f'{alg}_H'], rtol=1e-8, atol=1e-12)
+
+
+def test_cyclic_equals_full_batch(golden):
+    """tnmf/tests/test_minibatch.py:19-20."""
+    from tnmf_b200 import TransformInvariantNMF
+    g = golden('ref_minibatch')
+    np.random.seed(42)
+    nmf = TransformInvariantNMF(n_atoms=3, atom_shape=(4, 4))
+    nmf.fit_batch(g['V'], sparsity_H=0.1, n_iterations=5)
+    assert np.isclose(nmf._energy_function(), g['full_batch_E'], rtol=1e-9)
+    assert np.isclose(nmf._energy_function(), g['Cyclic_MU_E'], rtol=1e-9)
+    assert np.allclose(nmf.W, g['full_batch_W'], rtol=1e-8)
+
+
+def test_stream(golden):
+    """tnmf/tests/test_stream.py:47-108: array and generator input, with and without max_subsamples."""
+    from tnmf_b200 import MiniBatchAlgorithm, TransformInvariantNMF
+    g = golden('ref_minibatch')
+    np.random.seed(42)
+    nmf = TransformInvariantNMF(n_atoms=3, atom_shape=(4, 4))
+    nmf.fit(g['V'], subsample_size=3, batch_size=2, n_epochs=3, algorithm=MiniBatchAlgorithm.Cyclic_MU)
+    assert np.isclose(nmf._energy_function(), g['stream_E'], rtol=1e-9)
+    assert np.allclose(nmf.W, g['stream_W'], rtol=1e-8)
+    assert np.allclose(nmf.H, g['stream_H'], rtol=1e-8, atol=1e-12)
+    np.random.seed(42)
+    nmf = TransformInvariantNMF(n_atoms=3, atom_shape=(4, 4))
+    nmf.fit((v for v in g['V']), subsample_size=3, max_subsamples=2, n_iterations=4)
+    assert np.isclose(nmf._energy_function(), g['stream2_E'], rtol=1e-9)
+    assert np.allclose(nmf.W, g['stream2_W'], rtol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 1 (the reference's own CPU-runnable case), float64 and float32
+# ---------------------------------------------------------------------------------------------------------
+def test_cfg1_float64(golden):
+    from tnmf_b200 import TransformInvariantNMF
+    g = golden('ref_cfg1')
+    np.random.seed(42)
+    nmf = TransformInvariantNMF(n_atoms=5, atom_shape=(50,))
+    traj = []
+    nmf.fit(g['V'], n_iterations=100,
+            progress_callback=lambda m, i: (traj.append(m._energy_function()) if i % 10 == 9 else None) or True)
+    assert np.isclose(traj[-1], 3.808691, rtol=1e-6)                     # SURVEY 8c probe value
+    assert np.allclose(traj, g['E'][9::10], rtol=1e-8)
+    assert np.allclose(nmf.W, g['W'], rtol=1e-6, atol=1e-10)
+    assert np.allclose(nmf.H[:2, :, :64], g['H_head'], rtol=1e-6, atol=1e-10)
+
+
+def test_cfg1_float32_tiled(golden):
+    """Same run in float32 on the tiled kernels: energy within 1e-4 relative, W within 1e-3 of max|W|."""
+    from tnmf_b200 import TransformInvariantNMF
+    g = golden('ref_cfg1')
+    np.random.seed(42)
+    nmf = TransformInvariantNMF(n_atoms=5, atom_shape=(50,), kernel_path='tiled')
+    traj = []
+    nmf.fit(g['V'].astype(np.float32), n_iterations=100,
+            progress_callback=lambda m, i: (traj.append(m._energy_function()) if i % 10 == 9 else None) or True)
+    assert np.allclose(traj, g['E'][9::10], rtol=1e-4)
+    assert np.abs(nmf.W - g['W']).max() <= 1e-3 * np.abs(g['W']).max()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tiled kernels against the oracle on seeded inputs: shapes that exercise every tile edge
+# ---------------------------------------------------------------------------------------------------------
+TILED_CASES = [
+    # N, C, M, D, A
+    (2, 3, 4, (40, 70), (11, 11)),      # cfg2-like atoms, ragged tile edges
+    (3, 1, 5, (33, 65), (15, 15)),      # cfg3-like atoms, one past the tile size
+    (2, 1, 3, (20, 90), (7, 20)),       # atom wider than the ax-chunk (multi-chunk path)
+    (2, 2, 6, (1000,), (50,)),          # cfg1-like 1-D
+    (3, 1, 7, (300,), (128,)),          # cfg4-like 1-D atom
+    (1, 5, 2, (9, 9), (3, 2)),          # more channels than a channel block, even atom width
+    (4, 1, 1, (17, 13), (1, 1)),        # single atom of one pixel
+    (2, 2, 3, (6, 8), (6, 8)),          # atom as large as the sample ('full': a single activation)
+    (1, 1, 2, (70, 300), (5, 64)),      # wide atom, wide sample
+]
+
+
+@pytest.mark.parametrize('mode', MODES)
+@pytest.mark.parametrize('case', range(len(TILED_CASES)))
+def test_tiled_vs_oracle(case, mode):
+    N, C, M, D, A = TILED_CASES[case]
+    rng = np.random.default_rng(100 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'tiled')
+    assert be.uses_tiled_kernels()
+    tol = 2e-5
+    R = orc.reconstruct(W64, H64, mode)
+    _close(be.reconstruct(Wd, Hd), R, tol)
+    neg, pos = be.reconstruction_gradient_H(V, Wd, Hd)
+    rn, rp = orc.reconstruction_gradient_H(V64, W64, H64, mode)
+    _close(neg, rn, tol)
+    _close(pos, rp, tol)
+    neg, pos = be.reconstruction_gradient_W(V, Wd, Hd)
+    rn, rp = orc.reconstruction_gradient_W(V64, W64, H64, mode)
+    _close(neg, rn, tol)
+    _close(pos, rp, tol)
+    assert np.isclose(be.reconstruction_energy(V, Wd, Hd), orc.reconstruction_energy(V64, W64, H64, mode), rtol=2e-5)
+    # fused update with every epilogue term against the oracle's update
+    nmf = orc.OracleNMF(M, A, reconstruction_mode=mode)
+    nmf.V, nmf.W, nmf.H = V64, W64.copy(), H64.copy()
+    nmf.update_H(slice(None), sparsity=0.1, inhibition=0.2, cross_inhibition=0.3 if M > 1 else 0.0)
+    be.update_H(V, Wd, Hd, slice(None), 0.1, 0.2, 0.3 if M > 1 else 0.0, nmf.inhibition_kernels)
+    _close(Hd, nmf.H, 5e-5)
+    nmf.update_W()
+    grad = torch.empty((2, *Wd.shape), dtype=Wd.dtype, device=Wd.device)
+    be.apply_W_update(Wd, be.gradient_W(V, Wd, Hd, slice(None), grad))
+    _close(Wd, nmf.W, 5e-5)
+    assert np.allclose(Wd.sum(dim=tuple(range(2, Wd.dim()))).cpu().numpy(), 1.0, atol=1e-5)
+
+
+def test_empty_and_single_sample_batches():
+    """Ragged minibatches: an empty slice contributes a zero W gradient, a short last batch is served."""
+    rng = np.random.default_rng(7)
+    V = rng.random((3, 2, 12, 10)).astype(np.float32)
+    W = rng.random((3, 2, 4, 3)).astype(np.float32)
+    H = rng.random((3, 3, 15, 12)).astype(np.float32)
+    be, Wd, Hd = _backend(V, W, H)
+    grad = torch.full((2, *Wd.shape), 7.0, dtype=Wd.dtype, device=Wd.device)
+    be.gradient_W(V, Wd, Hd, slice(0, 0), grad)
+    assert float(grad.abs().max()) == 0.0
+    be.update_H(V, Wd, Hd, slice(0, 0))                      # no-op
+    _close(Hd, H, 0.0)
+    full = torch.empty_like(grad)
+    be.gradient_W(V, Wd, Hd, slice(None), full)
+    parts = torch.zeros_like(grad)
+    for s in (slice(0, 2), slice(2, 3)):
+        parts += be.gradient_W(V, Wd, Hd, s, torch.empty_like(grad))
+    _close(parts, full.cpu().numpy(), 1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE's full 2-D sizes (the oracle cannot run these)
+# ---------------------------------------------------------------------------------------------------------
+FULL_SIZE = {
+    'cfg2': dict(N=8, C=3, M=16, D=(256, 256), A=(11, 11)),        # full per-sample geometry, N reduced to 8
+    'cfg3': dict(N=16, C=1, M=32, D=(128, 128), A=(15, 15)),
+    'cfg4': dict(N=32, C=1, M=64, D=(4096,), A=(128,)),
+    'cfg5': dict(N=1, C=1, M=8, D=(512, 512), A=(64, 64)),
+}
+
+
+@pytest.mark.parametrize('name', list(FULL_SIZE))
+def test_trilinear_identities_at_full_size(name):
+    """All five hot-path tensors are partial derivatives of one trilinear form F(X, W, H):
+    <X, reconstruct(W,H)> = <H, negH(X)> = <W, negW(X)>, and reconstruct is linear in H.  Checked in float32 on
+    the tiled path at the full per-sample geometry of BASELINE configs 2-5."""
+    c = FULL_SIZE[name]
+    torch.manual_seed(1)
+    from tnmf_b200 import B200_Backend
+    be = B200_Backend(init='device', kernel_path='tiled')
+    dev = be.device
+    V = torch.rand((c['N'], c['C'], *c['D']), dtype=torch.float32, device=dev)
+    W, H = be.initialize(V, c['A'], c['M'], None, tuple(range(-len(c['A']), 0)))
+    assert be.uses_tiled_kernels()
+    R = be.reconstruct(W, H).clone()
+    f_r = float((V.double() * R.double()).sum())
+    neg, pos = be.reconstruction_gradient_H(V, W, H)
+    f_h = float((H.double() * neg.double()).sum())
+    f_hp = float((H.double() * pos.double()).sum())
+    negw, posw = be.reconstruction_gradient_W(V, W, H)
+    f_w = float((W.double() * negw.double()).sum())
+    f_wp = float((W.double() * posw.double()).sum())
+    rr = float((R.double() ** 2).sum())
+    assert np.isclose(f_h, f_r, rtol=2e-5) and np.isclose(f_w, f_r, rtol=2e-5)
+    assert np.isclose(f_hp, rr, rtol=2e-5) and np.isclose(f_wp, rr, rtol=2e-5)
+    # linearity in H
+    H2 = torch.rand_like(H)
+    R2 = be.reconstruct(W, H2).clone()
+    R12 = be.reconstruct(W, H + 2 * H2)
+    _close(R12, (R + 2 * R2).cpu().numpy(), 1e-5)
+    # energy = 0.5*||V - R||^2
+    e = be.reconstruction_energy(V, W, H)
+    assert np.isclose(e, 0.5 * float(((V.double() - R.double()) ** 2).sum()), rtol=1e-6)
+    # tiled and generic kernels agree on a sub-batch
+    bg = B200_Backend(init='device', kernel_path='generic')
+    n_sub = min(2, c['N'])
+    bg.initialize(V[:n_sub], c['A'], c['M'], None, tuple(range(-len(c['A']), 0)))
+    _close(bg.reconstruct(W, H[:n_sub]), R[:n_sub].cpu().numpy(), 2e-5)
+    # the MU keeps everything non-negative and the energy does not increase (Lee-Seung)
+    be.update_H(V, W, H)
+    grad = torch.empty((2, *W.shape), dtype=W.dtype, device=dev)
+    be.apply_W_update(W, be.gradient_W(V, W, H, slice(None), grad))
+    assert float(H.min()) >= 0 and float(W.min()) >= 0
+    assert np.allclose(W.sum(dim=tuple(range(2, W.dim()))).cpu().numpy(), 1.0, atol=1e-5)
+    assert be.reconstruction_energy(V, W, H) <= e * (1 + 1e-6)
+
+
+def test_missing_library_is_loud(monkeypatch):
+    """No silent fallback: without the shared object the binding refuses to load."""
+    from tnmf_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', '/nonexistent/libtnmf_b200.so')
+    with pytest.raises(ImportError):
+        _lib.load()
+
+
+def test_unsupported_requests_raise():
+    from tnmf_b200 import B200_Backend, TransformInvariantNMF
+    with pytest.raises(NotImplementedError):
+        B200_Backend(reconstruction_mode='reflect')
+    with pytest.raises(ValueError):
+        B200_Backend(reconstruction_mode='bogus')
+    with pytest.raises(ValueError):
+        TransformInvariantNMF(2, (3,), backend='numpy')
+    be = B200_Backend(kernel_path='tiled')
+    V = np.random.default_rng(0).random((1, 1, 4, 4, 4))
+    with pytest.raises(NotImplementedError):                 # three shift axes in float64 have no tiled kernel
+        W, H = be.initialize(V, (2, 2, 2), 2, None, (-3, -2, -1))
+        be.reconstruct(W, H)

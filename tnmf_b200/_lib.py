@@ -1,0 +1,156 @@
+"""
+ctypes binding of libtnmf_b200.so (the C-ABI declared in include/tnmf_b200.h) and its in-tree build recipe.
+
+The library is the only arithmetic provider of this package: there is no CPU fallback and no alternative
+code path.  If the shared object is missing or does not export the declared symbols, importing the binding
+fails loudly.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+from typing import Optional, Sequence
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB_PATH = os.path.join(HERE, 'libtnmf_b200.so')
+SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu')
+HEADERS = ('common.cuh', os.path.join('..', '..', 'include', 'tnmf_b200.h'))
+
+# NB: no --use_fast_math: divisions must round like the reference's IEEE arithmetic.
+NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '-Xcompiler', '-fPIC')
+
+TNMF_F32, TNMF_F64 = 0, 1
+MODES = {'valid': 0, 'full': 1, 'circular': 2}
+PATHS = {'auto': 0, 'generic': 1, 'tiled': 2}
+TNMF_OK, TNMF_EINVAL, TNMF_EUNSUPPORTED, TNMF_EWORKSPACE, TNMF_ECUDA = 0, 1, 2, 3, 1000
+ABI_VERSION = 1
+
+
+class Problem(ctypes.Structure):
+    """Mirror of `struct tnmf_problem` (include/tnmf_b200.h)."""
+    _fields_ = [
+        ('ndim', ctypes.c_int32), ('dtype', ctypes.c_int32), ('mode', ctypes.c_int32), ('path', ctypes.c_int32),
+        ('n_samples', ctypes.c_int32), ('n_channels', ctypes.c_int32), ('n_atoms', ctypes.c_int32),
+        ('reserved', ctypes.c_int32),
+        ('sample_shape', ctypes.c_int32 * 3), ('atom_shape', ctypes.c_int32 * 3),
+        ('h_stride_n', ctypes.c_int64), ('h_stride_m', ctypes.c_int64),
+    ]
+
+
+_P = ctypes.POINTER(Problem)
+_vp, _i32, _i64, _dbl, _sz = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_size_t
+
+# name -> (restype, argtypes); every symbol include/tnmf_b200.h declares
+SIGNATURES = {
+    'tnmf_abi_version': (ctypes.c_int, []),
+    'tnmf_status_string': (ctypes.c_char_p, [ctypes.c_int]),
+    'tnmf_transform_shape': (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32)]),
+    'tnmf_workspace_bytes': (_sz, [_P]),
+    'tnmf_uses_tiled_path': (ctypes.c_int, [_P]),
+    'tnmf_reconstruct': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp]),
+    'tnmf_reconstruct_energy': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'tnmf_gradient_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'tnmf_update_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _dbl, _vp, _dbl, _vp, _dbl, _vp]),
+    'tnmf_gradient_w': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'tnmf_update_w': (ctypes.c_int, [_P, _vp, _vp, _vp, _dbl, _vp]),
+    'tnmf_normalize': (ctypes.c_int, [_i32, _vp, _i64, _i64, _i64, _vp]),
+    'tnmf_convolve_1d': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp]),
+    'tnmf_sum_atoms': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i64, _i64, _vp]),
+    'tnmf_fp32_peak_probe': (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ctypes.c_double), _vp]),
+}
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into tnmf_b200/libtnmf_b200.so (in-tree, travels with the repo)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found: cannot build libtnmf_b200.so')
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(HERE, '_obj'), exist_ok=True)
+    for s in SOURCES:
+        obj = os.path.join(HERE, '_obj', s.replace('.cu', '.o'))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, '-Xptxas', '-v', '-c', os.path.join(CSRC, s), '-o', obj]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    for s, pr in procs:
+        out, _ = pr.communicate()
+        log.append(f'== {s}\n{out}')
+        if pr.returncode != 0:
+            raise RuntimeError(f'nvcc failed on {s}:\n{out}')
+    with open(os.path.join(HERE, '_obj', 'ptxas.log'), 'w') as f:
+        f.write('\n'.join(log))
+    if verbose:
+        print('\n'.join(log))
+    tmp = LIB_PATH + '.tmp'
+    subprocess.run([nvcc, '-shared', '-o', tmp, *objs, '-lcudart'], check=True)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared object and bind every declared symbol.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                          f'(tnmf_b200 has no CPU fallback)')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.tnmf_abi_version() != ABI_VERSION:
+        raise ImportError(f'libtnmf_b200.so has ABI {lib.tnmf_abi_version()}, binding expects {ABI_VERSION}')
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = '') -> None:
+    """Translate a status code into the reference's error conventions."""
+    if status == TNMF_OK:
+        return
+    msg = load().tnmf_status_string(status).decode()
+    if what:
+        msg = f'{what}: {msg}'
+    if status == TNMF_EUNSUPPORTED:
+        raise NotImplementedError(msg)
+    if status == TNMF_EINVAL:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def make_problem(n_samples: int, n_channels: int, n_atoms: int, sample_shape: Sequence[int],
+                 atom_shape: Sequence[int], dtype_code: int, mode: str = 'valid', path: str = 'auto',
+                 h_stride_n: int = 0, h_stride_m: int = 0) -> Problem:
+    if mode not in MODES:
+        raise ValueError(f'Unsupported reconstruction mode "{mode}". Please choose "valid", "full" or "circular".')
+    if len(sample_shape) != len(atom_shape):
+        raise ValueError('sample and atom rank differ')
+    if not 1 <= len(sample_shape) <= 3:
+        raise NotImplementedError('tnmf_b200 supports 1 to 3 shift axes')
+    p = Problem()
+    p.ndim, p.dtype, p.mode, p.path = len(sample_shape), dtype_code, MODES[mode], PATHS[path]
+    p.n_samples, p.n_channels, p.n_atoms = int(n_samples), int(n_channels), int(n_atoms)
+    for i, (d, a) in enumerate(zip(sample_shape, atom_shape)):
+        p.sample_shape[i] = int(d)
+        p.atom_shape[i] = int(a)
+    p.h_stride_n, p.h_stride_m = int(h_stride_n), int(h_stride_m)
+    return p

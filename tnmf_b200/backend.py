@@ -1,0 +1,392 @@
+"""
+`B200_Backend`: the B200-native implementation of tnmf's backend interface.
+
+It sits next to the reference's numpy / numpy_fft / numpy_caching_fft / pytorch backends
+(tnmf/backends/*.py) behind the same abstract class (tnmf/backends/_Backend.py:13-130).  All arithmetic is done
+by the hand-written sm_100a kernels of libtnmf_b200.so, reached through the C-ABI in include/tnmf_b200.h;
+PyTorch only owns the device buffers and the stream.  There is no CPU fallback: without a CUDA device or
+without the shared object every operation raises.
+
+Two groups of methods:
+  * the reference interface proper (`initialize`, `reconstruct`, `reconstruction_gradient_H/W`,
+    `reconstruction_energy`, `normalize`, `convolve_multi_1d`, `to_ndarray`, `partial_reconstruct`), which the
+    stock facade can drive unchanged, and
+  * fused entry points (`update_H`, `gradient_W`, `apply_W_update`, `energy`) used by
+    `tnmf_b200.TransformInvariantNMF`, which fold the facade's multiplicative-update arithmetic
+    (tnmf/TransformInvariantNMF.py:217-271) into the kernels' epilogues.
+"""
+import ctypes
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .interface import Backend, sliceNone
+
+_DTYPE_CODE = {torch.float32: _lib.TNMF_F32, torch.float64: _lib.TNMF_F64}
+_NP_TO_TORCH = {np.dtype('float32'): torch.float32, np.dtype('float64'): torch.float64}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class B200_Backend(Backend):  # pylint: disable=invalid-name
+    r"""
+    Parameters
+    ----------
+    reconstruction_mode : 'valid' (default), 'full' or 'circular'
+        As in the reference (tnmf/backends/_Backend.py:22-26, 60-73).  'reflect' is not pinned by the reference's
+        own tests and raises NotImplementedError, the convention of tnmf/backends/NumPy.py:26-27.
+    device : torch device, default: current CUDA device
+    init : 'numpy' (default) draws H then W from the global legacy numpy RNG exactly like
+        tnmf/backends/_Backend.py:83-98 (bit-identical seeded initialisation); 'device' draws them with the
+        device RNG (for problem sizes whose float64 host draw would not fit host memory).
+    kernel_path : 'auto' | 'generic' | 'tiled'   (diagnostics; see include/tnmf_b200.h)
+    """
+
+    def __init__(self, reconstruction_mode: str = 'valid', device=None, init: str = 'numpy',
+                 kernel_path: str = 'auto'):
+        super().__init__(reconstruction_mode=reconstruction_mode)
+        if reconstruction_mode in ('reflect', 'same'):
+            raise NotImplementedError(f'reconstruction mode "{reconstruction_mode}" is not provided by the b200 backend')
+        if reconstruction_mode not in _lib.MODES:
+            raise ValueError(f'Unsupported reconstruction mode "{reconstruction_mode}". '
+                             f'Please choose "valid", "full" or "circular".')
+        if init not in ('numpy', 'device'):
+            raise ValueError('init must be "numpy" or "device"')
+        if kernel_path not in _lib.PATHS:
+            raise ValueError('kernel_path must be one of ' + ', '.join(_lib.PATHS))
+        if not torch.cuda.is_available():
+            raise RuntimeError('the b200 backend needs a CUDA device (it has no CPU fallback)')
+        self._lib = _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
+        self._init = init
+        self._path = kernel_path
+        self.n_atoms = None
+        self._dtype = None
+        self._V_src = None      # the object the caller passes as V ...
+        self._V_dev = None      # ... and its device copy
+        self._R_buf = None
+        self._ws = None
+        self._energy_buf = None
+        self._problems = {}
+        self._taps = {}
+        self.launches = 0       # number of kernels of this library launched so far (bench.py reports it)
+
+    # -----------------------------------------------------------------------------------------------
+    # plumbing
+    # -----------------------------------------------------------------------------------------------
+    def _to_device(self, arr, dtype=None) -> torch.Tensor:
+        if isinstance(arr, torch.Tensor):
+            t = arr
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(arr))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        return t.contiguous()
+
+    def _device_V(self, V) -> torch.Tensor:
+        """Device copy of V.  Like the reference's caching backends (tnmf/backends/NumPy.py:53,101,
+        NumPy_CachingFFT.py:259,273) the copy made at `initialize` is reused while the same object is passed."""
+        if isinstance(V, torch.Tensor) and V.device == self.device and V.is_contiguous():
+            return V
+        if V is self._V_src and self._V_dev is not None:
+            return self._V_dev
+        dev = self._to_device(V, self._dtype)
+        self._V_src, self._V_dev = V, dev
+        return dev
+
+    def _problem(self, n: int, n_atoms: int, hsn: int = 0, hsm: int = 0) -> _lib.Problem:
+        key = (n, n_atoms, hsn, hsm)
+        p = self._problems.get(key)
+        if p is None:
+            p = _lib.make_problem(n, self.n_channels, n_atoms, self._sample_shape, self.atom_shape,
+                                  _DTYPE_CODE[self._dtype], self._reconstruction_mode, self._path, hsn, hsm)
+            self._problems[key] = p
+        return p
+
+    def _h_problem(self, H: torch.Tensor) -> Tuple[_lib.Problem, torch.Tensor]:
+        """Problem descriptor for an activation tensor that may be a view (leading-axis slice, single atom)."""
+        k = len(self.atom_shape)
+        tail = H.shape[2:]
+        expect = 1
+        ok = True
+        for size, stride in zip(reversed(tail), reversed(H.stride()[2:])):
+            if size != 1 and stride != expect:
+                ok = False
+            expect *= size
+        if not ok:
+            H = H.contiguous()
+        assert len(tail) == k
+        hsn, hsm = max(int(H.stride(0)), 1), max(int(H.stride(1)), 1)   # strides of size-1 axes are never used
+        return self._problem(H.shape[0], H.shape[1], hsn, hsm), H
+
+    def _workspace(self, p: _lib.Problem) -> Tuple[torch.Tensor, int]:
+        need = int(self._lib.tnmf_workspace_bytes(ctypes.byref(p)))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+        return self._ws, self._ws.numel()
+
+    def _R_for(self, n: int) -> torch.Tensor:
+        shape = (n, self.n_channels, *self._sample_shape)
+        numel = int(np.prod(shape))
+        if self._R_buf is None or self._R_buf.numel() < numel or self._R_buf.dtype != self._dtype:
+            self._R_buf = torch.empty(max(numel, 1), dtype=self._dtype, device=self.device)
+        return self._R_buf[:numel].view(shape)
+
+    def uses_tiled_kernels(self, n: Optional[int] = None) -> bool:
+        p = self._problem(self.n_samples if n is None else n, self.n_atoms)
+        return bool(self._lib.tnmf_uses_tiled_path(ctypes.byref(p)))
+
+    # -----------------------------------------------------------------------------------------------
+    # reference interface: initialisation (tnmf/backends/_Backend.py:35-98)
+    # -----------------------------------------------------------------------------------------------
+    def _set_dimensions(self, V, atom_shape):
+        self.atom_shape = tuple(int(a) for a in atom_shape)
+        self.n_samples = int(V.shape[0])
+        self.n_channels = int(V.shape[1])
+        self._sample_shape = tuple(int(d) for d in V.shape[2:])
+        if len(self._sample_shape) != len(self.atom_shape):
+            raise ValueError('atom_shape and the sample shape must have the same number of shift axes')
+        p = _lib.make_problem(1, 1, 1, self._sample_shape, self.atom_shape, 0, self._reconstruction_mode)
+        t = (ctypes.c_int32 * 3)()
+        _lib.check(self._lib.tnmf_transform_shape(ctypes.byref(p), t), 'transform shape')
+        self._transform_shape = tuple(int(t[i]) for i in range(len(self.atom_shape)))
+        self._n_shift_dimensions = len(self.atom_shape)
+        self._shift_dimensions = tuple(range(-1, -len(self.atom_shape) - 1, -1))
+        self._problems = {}
+
+    def initialize(self, V, atom_shape: Tuple[int, ...], n_atoms: int, W=None,
+                   axes_W_normalization: Optional[Union[int, Tuple[int, ...]]] = None,
+                   sample_range: Optional[Tuple[int, int]] = None):
+        """Allocate H (and W unless one is handed back in, `keep_W`), upload V.
+
+        `sample_range=(lo, hi)` keeps only that block of samples on this device (multi-GPU sample sharding);
+        with init='numpy' the random draw still covers all samples so that every shard sees exactly the
+        numbers a single-device run would."""
+        n_total = int(V.shape[0])
+        lo, hi = (0, n_total) if sample_range is None else sample_range
+        if isinstance(V, torch.Tensor):
+            if V.dtype not in _DTYPE_CODE:
+                raise NotImplementedError(f'dtype {V.dtype} is not supported (float32 / float64)')
+            self._dtype = V.dtype
+        else:
+            if np.dtype(V.dtype) not in _NP_TO_TORCH:
+                raise NotImplementedError(f'dtype {V.dtype} is not supported (float32 / float64)')
+            self._dtype = _NP_TO_TORCH[np.dtype(V.dtype)]
+        V_local = V if sample_range is None else V[lo:hi]
+        self._set_dimensions(V_local, atom_shape)
+        self.n_atoms = int(n_atoms)
+        self._V_src, self._V_dev = None, None
+        self._V_src, self._V_dev = V, self._to_device(V_local, self._dtype)
+
+        h_shape = (hi - lo, self.n_atoms, *self._transform_shape)
+        w_shape = (self.n_atoms, self.n_channels, *self.atom_shape)
+        if self._init == 'numpy':
+            # identical stream of random numbers as the reference: H first, then W, float64 draws cast to V.dtype
+            np_dtype = np.float32 if self._dtype == torch.float32 else np.float64
+            h_host = np.asarray(1 - np.random.rand(n_total, self.n_atoms, *self._transform_shape), dtype=np_dtype)
+            H = self._to_device(h_host[lo:hi])
+            del h_host
+            if W is None:
+                w_host = np.asarray(1 - np.random.rand(*w_shape), dtype=np_dtype)
+                W = self._to_device(w_host)
+                self.normalize(W, axes_W_normalization)
+        else:
+            H = 1 - torch.rand(h_shape, dtype=self._dtype, device=self.device)
+            if W is None:
+                W = 1 - torch.rand(w_shape, dtype=self._dtype, device=self.device)
+                self.normalize(W, axes_W_normalization)
+        if not isinstance(W, torch.Tensor) or W.device != self.device:
+            W = self._to_device(W, self._dtype)          # a W kept from a run of another backend
+        if tuple(W.shape) != w_shape:
+            raise ValueError(f'W has shape {tuple(W.shape)}, expected {w_shape}')
+        return W, H
+
+    @staticmethod
+    def to_ndarray(arr) -> np.ndarray:
+        if isinstance(arr, torch.Tensor):
+            return arr.detach().cpu().numpy()
+        return np.asarray(arr)
+
+    # -----------------------------------------------------------------------------------------------
+    # reference interface: small helpers
+    # -----------------------------------------------------------------------------------------------
+    @staticmethod
+    def normalize(arr: torch.Tensor, axis: Optional[Union[int, Tuple[int, ...]]] = None):
+        """In place arr /= arr.sum(axis, keepdims=True)   (tnmf/backends/_Backend.py:75-77)."""
+        nd = arr.dim()
+        if axis is None:
+            axes = tuple(range(nd))
+        elif isinstance(axis, int):
+            axes = (axis % nd,)
+        else:
+            axes = tuple(sorted(a % nd for a in axis))
+        if not arr.is_cuda or not arr.is_contiguous() or arr.dtype not in _DTYPE_CODE \
+                or axes != tuple(range(axes[0], axes[-1] + 1)):
+            raise NotImplementedError('normalize needs a contiguous CUDA tensor and adjacent axes')
+        outer = int(np.prod(arr.shape[:axes[0]], dtype=np.int64))
+        length = int(np.prod(arr.shape[axes[0]:axes[-1] + 1], dtype=np.int64))
+        inner = int(np.prod(arr.shape[axes[-1] + 1:], dtype=np.int64))
+        lib = _lib.load()
+        _lib.check(lib.tnmf_normalize(_DTYPE_CODE[arr.dtype], arr.data_ptr(), outer, length, inner,
+                                      _stream_ptr(arr.device)), 'normalize')
+
+    @staticmethod
+    def convolve_multi_1d(arr: torch.Tensor, kernels: Sequence[np.ndarray], axes: Sequence[int]) -> torch.Tensor:
+        """Separable zero-boundary convolution (tnmf/backends/_NumPyBackend.py:56-64)."""
+        assert len(kernels) == len(axes)
+        lib = _lib.load()
+        src = arr if arr.is_contiguous() else arr.contiguous()
+        code = _DTYPE_CODE[src.dtype]
+        out = src
+        for a, kern in zip(axes, kernels):
+            a = a % src.dim()
+            taps = torch.as_tensor(np.ascontiguousarray(kern, dtype=np.float64)).to(src.device)
+            dst = torch.empty_like(src)
+            outer = int(np.prod(src.shape[:a], dtype=np.int64))
+            inner = int(np.prod(src.shape[a + 1:], dtype=np.int64))
+            _lib.check(lib.tnmf_convolve_1d(code, out.data_ptr(), dst.data_ptr(), outer, int(src.shape[a]), inner,
+                                            taps.data_ptr(), int(taps.numel()), _stream_ptr(src.device)),
+                       'convolve_multi_1d')
+            out = dst
+        if out is arr:
+            out = arr.clone()
+        return out
+
+    # -----------------------------------------------------------------------------------------------
+    # reference interface: the four hot-path operations
+    # -----------------------------------------------------------------------------------------------
+    def reconstruct(self, W: torch.Tensor, H: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """R = sum_m W[m] * H[:, m]   (tnmf/backends/_Backend.py:120-122).  Accepts H views (partial_reconstruct)."""
+        p, H = self._h_problem(H)
+        if W.shape[0] != H.shape[1]:
+            raise ValueError('W and H disagree on the number of atoms')
+        W = W if W.is_contiguous() else W.contiguous()
+        R = out if out is not None else torch.empty((H.shape[0], self.n_channels, *self._sample_shape),
+                                                    dtype=self._dtype, device=self.device)
+        _lib.check(self._lib.tnmf_reconstruct(ctypes.byref(p), W.data_ptr(), H.data_ptr(), R.data_ptr(),
+                                              _stream_ptr(self.device)), 'reconstruct')
+        self.launches += 1
+        return R
+
+    def reconstruction_gradient_H(self, V, W, H, s: slice = sliceNone):
+        """(neg, pos) with the shape of H[s]   (tnmf/backends/_Backend.py:110-118)."""
+        Hs = H[s]
+        Vs = self._device_V(V)[s]
+        R = self.reconstruct(W, Hs, out=self._R_for(Hs.shape[0]))
+        p = self._problem(Hs.shape[0], self.n_atoms)
+        neg = torch.empty(Hs.shape, dtype=self._dtype, device=self.device)
+        pos = torch.empty_like(neg)
+        _lib.check(self._lib.tnmf_gradient_h(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), W.data_ptr(),
+                                             neg.data_ptr(), pos.data_ptr(), _stream_ptr(self.device)), 'gradient_h')
+        self.launches += 1
+        return neg, pos
+
+    def reconstruction_gradient_W(self, V, W, H, s: slice = sliceNone):
+        """(neg, pos) with the shape of W   (tnmf/backends/_Backend.py:100-108)."""
+        out = torch.empty((2, *W.shape), dtype=self._dtype, device=self.device)
+        self.gradient_W(V, W, H, s, out)
+        return out[0], out[1]
+
+    def reconstruction_energy(self, V, W, H) -> float:
+        """0.5 * ||V - R||^2 as a Python float   (tnmf/backends/_Backend.py:127-130)."""
+        return float(self.energy(V, W, H).item())
+
+    # -----------------------------------------------------------------------------------------------
+    # fused entry points used by tnmf_b200.TransformInvariantNMF
+    # -----------------------------------------------------------------------------------------------
+    def energy(self, V, W, H, s: slice = sliceNone) -> torch.Tensor:
+        """Device-resident double scalar 0.5*||V[s] - reconstruct(W, H[s])||^2 (no host synchronisation)."""
+        Hs = H[s]
+        Vs = self._device_V(V)[s]
+        p, Hs = self._h_problem(Hs)
+        ws, ws_bytes = self._workspace(p)
+        e = torch.empty((), dtype=torch.float64, device=self.device)
+        _lib.check(self._lib.tnmf_reconstruct_energy(ctypes.byref(p), Vs.data_ptr(), W.data_ptr(), Hs.data_ptr(), None,
+                                                     e.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(self.device)),
+                   'reconstruct_energy')
+        self.launches += 2
+        return e
+
+    def _inhibition_taps(self, kernels: Sequence[np.ndarray]):
+        key = tuple(k.tobytes() for k in kernels)
+        taps = self._taps.get(key)
+        if taps is None:
+            taps = [torch.as_tensor(np.ascontiguousarray(k, dtype=np.float64)).to(self.device) for k in kernels]
+            self._taps = {key: taps}
+        return taps
+
+    def update_H(self, V, W, H, s: slice = sliceNone, sparsity: float = 0., inhibition: float = 0.,
+                 cross_inhibition: float = 0., inhibition_kernels: Optional[Sequence[np.ndarray]] = None,
+                 eps: float = 1.e-9) -> None:
+        """One in-place multiplicative update of H[s]: reconstruct, both correlations, sparsity / inhibition terms and
+        H <- (H*neg)/pos in one fused kernel   (tnmf/TransformInvariantNMF.py:246-271 + :217-235)."""
+        Hs = H[s]
+        if Hs.shape[0] == 0:
+            return
+        assert Hs.is_contiguous()
+        Vs = self._device_V(V)[s]
+        n = Hs.shape[0]
+        R = self.reconstruct(W, Hs, out=self._R_for(n))
+        p = self._problem(n, self.n_atoms)
+        G_ptr, Gsum_ptr = None, None
+        lam, lam_cross = 0.0, 0.0
+        st = _stream_ptr(self.device)
+        if inhibition > 0 or cross_inhibition > 0:
+            taps = self._inhibition_taps(inhibition_kernels)
+            code = _DTYPE_CODE[self._dtype]
+            G = Hs
+            k = len(self.atom_shape)
+            for i, tp in enumerate(taps):
+                axis = Hs.dim() - k + i
+                dst = torch.empty_like(Hs)
+                outer = int(np.prod(Hs.shape[:axis], dtype=np.int64))
+                inner = int(np.prod(Hs.shape[axis + 1:], dtype=np.int64))
+                _lib.check(self._lib.tnmf_convolve_1d(code, G.data_ptr(), dst.data_ptr(), outer, int(Hs.shape[axis]),
+                                                      inner, tp.data_ptr(), int(tp.numel()), st), 'convolve_1d')
+                self.launches += 1
+                G = dst
+            G_ptr = G.data_ptr()
+            lam = float(inhibition) if inhibition > 0 else 0.0
+            if cross_inhibition > 0:
+                inner = int(np.prod(Hs.shape[2:], dtype=np.int64))
+                Gsum = torch.empty((n, 1, *Hs.shape[2:]), dtype=self._dtype, device=self.device)
+                _lib.check(self._lib.tnmf_sum_atoms(code, G.data_ptr(), Gsum.data_ptr(), n, self.n_atoms, inner, st),
+                           'sum_atoms')
+                self.launches += 1
+                Gsum_ptr = Gsum.data_ptr()
+                lam_cross = float(cross_inhibition) / (self.n_atoms - 1)
+        reg = eps + sparsity if sparsity > 0 else eps
+        _lib.check(self._lib.tnmf_update_h(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), W.data_ptr(), Hs.data_ptr(),
+                                           float(reg), G_ptr, lam, Gsum_ptr, lam_cross, st), 'update_h')
+        self.launches += 1
+
+    def gradient_W(self, V, W, H, s: slice, out: torch.Tensor) -> torch.Tensor:
+        """out[0] = neg, out[1] = pos of the W gradient on samples s (split-K + deterministic final reduction)."""
+        Hs = H[s]
+        Vs = self._device_V(V)[s]
+        n = Hs.shape[0]
+        p, Hs = self._h_problem(Hs)
+        if n == 0:
+            out.zero_()
+            return out
+        R = self.reconstruct(W, Hs, out=self._R_for(n))
+        ws, ws_bytes = self._workspace(p)
+        _lib.check(self._lib.tnmf_gradient_w(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), Hs.data_ptr(),
+                                             out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws_bytes,
+                                             _stream_ptr(self.device)), 'gradient_w')
+        self.launches += 2
+        return out
+
+    def apply_W_update(self, W: torch.Tensor, grad: torch.Tensor, eps: float = 1.e-9) -> None:
+        """W <- (W*neg)/(pos+eps), then per-(atom, channel) normalisation, in place
+        (tnmf/TransformInvariantNMF.py:217-244, tnmf/backends/_Backend.py:75-77).  grad = stacked (neg, pos)."""
+        p = self._problem(0, self.n_atoms)
+        _lib.check(self._lib.tnmf_update_w(ctypes.byref(p), W.data_ptr(), grad[0].data_ptr(), grad[1].data_ptr(),
+                                           float(eps), _stream_ptr(self.device)), 'update_w')
+        self.launches += 1

@@ -1,0 +1,264 @@
+// extern "C" surface of libtnmf_b200.so: argument validation, geometry set-up and kernel-family dispatch.
+// See include/tnmf_b200.h for the contract of every entry point and the reference interface it replaces.
+#include <cstdio>
+#include <cstring>
+#include "common.cuh"
+
+using namespace tnmf;
+
+namespace {
+
+int make_geo(const tnmf_problem *p, Geo &g) {
+    if (!p) return TNMF_EINVAL;
+    if (p->ndim < 1 || p->ndim > TNMF_MAX_SHIFT_DIMS) return TNMF_EUNSUPPORTED;
+    if (p->dtype != TNMF_F32 && p->dtype != TNMF_F64) return TNMF_EUNSUPPORTED;
+    if (p->mode != TNMF_VALID && p->mode != TNMF_FULL && p->mode != TNMF_CIRCULAR) return TNMF_EINVAL;
+    if (p->n_samples < 0 || p->n_channels < 1 || p->n_atoms < 1) return TNMF_EINVAL;
+    g.N = p->n_samples; g.C = p->n_channels; g.M = p->n_atoms; g.ndim = p->ndim;
+    g.wrap = p->mode == TNMF_CIRCULAR;
+    const int lead = 3 - p->ndim;
+    for (int i = 0; i < 3; ++i) { g.D[i] = 1; g.A[i] = 1; g.T[i] = 1; g.off[i] = 0; }
+    for (int i = 0; i < p->ndim; ++i) {
+        const int d = p->sample_shape[i], a = p->atom_shape[i];
+        if (d < 1 || a < 1) return TNMF_EINVAL;
+        int t;
+        if (p->mode == TNMF_VALID) t = d + a - 1;
+        else if (p->mode == TNMF_FULL) t = d - a + 1;
+        else t = d;
+        if (t < 1) return TNMF_EINVAL;
+        g.D[lead + i] = d; g.A[lead + i] = a; g.T[lead + i] = t;
+        g.off[lead + i] = p->mode == TNMF_VALID ? a - 1 : 0;
+    }
+    const long long tvol = vol3(g.T);
+    g.hsm = p->h_stride_m ? p->h_stride_m : tvol;
+    g.hsn = p->h_stride_n ? p->h_stride_n : tvol * g.M;
+    return TNMF_OK;
+}
+
+bool use_tiled(const tnmf_problem *p, const Geo &g, int *err) {
+    *err = TNMF_OK;
+    const bool ok = tiled_supported(g, p->dtype);
+    if (p->path == TNMF_PATH_GENERIC) return false;
+    if (p->path == TNMF_PATH_TILED) {
+        if (!ok) *err = TNMF_EUNSUPPORTED;
+        return ok;
+    }
+    return ok;
+}
+
+size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+size_t energy_partials_bytes(const Geo &g) {
+    return align256(sizeof(double) * (size_t)generic_energy_partial_capacity(g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int tnmf_abi_version(void) { return TNMF_ABI_VERSION; }
+
+const char *tnmf_status_string(int status) {
+    static thread_local char buf[160];
+    switch (status) {
+        case TNMF_OK: return "ok";
+        case TNMF_EINVAL: return "invalid argument";
+        case TNMF_EUNSUPPORTED: return "unsupported problem (no kernel, and there is no CPU fallback)";
+        case TNMF_EWORKSPACE: return "workspace too small";
+        default: break;
+    }
+    if (status >= TNMF_ECUDA) {
+        snprintf(buf, sizeof(buf), "CUDA error %d: %s", status - TNMF_ECUDA,
+                 cudaGetErrorString((cudaError_t)(status - TNMF_ECUDA)));
+        return buf;
+    }
+    return "unknown status";
+}
+
+int tnmf_transform_shape(const tnmf_problem *p, int32_t *t_shape) {
+    Geo g;
+    int s = make_geo(p, g);
+    if (s) return s;
+    if (!t_shape) return TNMF_EINVAL;
+    for (int i = 0; i < p->ndim; ++i) t_shape[i] = g.T[3 - p->ndim + i];
+    return TNMF_OK;
+}
+
+size_t tnmf_workspace_bytes(const tnmf_problem *p) {
+    Geo g;
+    if (make_geo(p, g)) return 0;
+    size_t bytes = energy_partials_bytes(g);
+    if (tiled_supported(g, p->dtype)) {
+        const size_t t = align256(tiled_workspace_bytes(g));
+        if (t > bytes) bytes = t;
+    }
+    return bytes;
+}
+
+int tnmf_uses_tiled_path(const tnmf_problem *p) {
+    Geo g;
+    if (make_geo(p, g)) return 0;
+    int err;
+    return use_tiled(p, g, &err) ? 1 : 0;
+}
+
+int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *R, void *stream) {
+    Geo g;
+    int s = make_geo(p, g);
+    if (s) return s;
+    if (!W || !H || !R) return TNMF_EINVAL;
+    if (g.N == 0) return TNMF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tiled = use_tiled(p, g, &s);
+    if (s) return s;
+    if (tiled)
+        return tiled_reconstruct(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
+    if (p->dtype == TNMF_F32)
+        return generic_reconstruct<float>(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr,
+                                          nullptr, st);
+    return generic_reconstruct<double>(g, (const double *)W, (const double *)H, (double *)R, nullptr, nullptr,
+                                       nullptr, st);
+}
+
+int tnmf_reconstruct_energy(const tnmf_problem *p, const void *V, const void *W, const void *H, void *R,
+                            double *energy, void *workspace, size_t workspace_bytes, void *stream) {
+    Geo g;
+    int s = make_geo(p, g);
+    if (s) return s;
+    if (!V || !W || !H || !energy || !workspace) return TNMF_EINVAL;
+    if (workspace_bytes < tnmf_workspace_bytes(p)) return TNMF_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    double *partials = (double *)workspace;
+    int n_partials = 0;
+    if (g.N == 0) {
+        cudaError_t e = cudaMemsetAsync(energy, 0, sizeof(double), st);
+        return status_from_cuda(e);
+    }
+    const bool tiled = use_tiled(p, g, &s);
+    if (s) return s;
+    if (tiled)
+        s = tiled_reconstruct(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials,
+                              &n_partials, st);
+    else if (p->dtype == TNMF_F32)
+        s = generic_reconstruct<float>(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials,
+                                       &n_partials, st);
+    else
+        s = generic_reconstruct<double>(g, (const double *)W, (const double *)H, (double *)R, (const double *)V,
+                                        partials, &n_partials, st);
+    if (s) return s;
+    return finish_energy(partials, n_partials, energy, st);
+}
+
+static int gradient_h_dispatch(const tnmf_problem *p, const void *V, const void *R, const void *W, void *neg,
+                               void *pos, void *H, double reg, const void *G, double lambda, const void *Gsum,
+                               double lambda_cross, void *stream) {
+    Geo g;
+    int s = make_geo(p, g);
+    if (s) return s;
+    if (!V || !R || !W) return TNMF_EINVAL;
+    if (g.N == 0) return TNMF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool tiled = use_tiled(p, g, &s);
+    if (s) return s;
+    if (tiled)
+        return tiled_gradient_h(g, (const float *)V, (const float *)R, (const float *)W, (float *)neg, (float *)pos,
+                                (float *)H, reg, (const float *)G, lambda, (const float *)Gsum, lambda_cross, st);
+    if (p->dtype == TNMF_F32)
+        return generic_gradient_h<float>(g, (const float *)V, (const float *)R, (const float *)W, (float *)neg,
+                                         (float *)pos, (float *)H, reg, (const float *)G, lambda,
+                                         (const float *)Gsum, lambda_cross, st);
+    return generic_gradient_h<double>(g, (const double *)V, (const double *)R, (const double *)W, (double *)neg,
+                                      (double *)pos, (double *)H, reg, (const double *)G, lambda,
+                                      (const double *)Gsum, lambda_cross, st);
+}
+
+int tnmf_gradient_h(const tnmf_problem *p, const void *V, const void *R, const void *W, void *neg, void *pos,
+                    void *stream) {
+    if (!neg || !pos) return TNMF_EINVAL;
+    return gradient_h_dispatch(p, V, R, W, neg, pos, nullptr, 0.0, nullptr, 0.0, nullptr, 0.0, stream);
+}
+
+int tnmf_update_h(const tnmf_problem *p, const void *V, const void *R, const void *W, void *H, double reg,
+                  const void *G, double lambda, const void *Gsum, double lambda_cross, void *stream) {
+    if (!H) return TNMF_EINVAL;
+    if (lambda_cross != 0.0 && !Gsum) return TNMF_EINVAL;
+    if (lambda_cross == 0.0) Gsum = nullptr;
+    if (lambda == 0.0 && !Gsum) G = nullptr;
+    if ((lambda != 0.0 || Gsum) && !G) return TNMF_EINVAL;
+    return gradient_h_dispatch(p, V, R, W, nullptr, nullptr, H, reg, G, lambda, Gsum, lambda_cross, stream);
+}
+
+int tnmf_gradient_w(const tnmf_problem *p, const void *V, const void *R, const void *H, void *neg, void *pos,
+                    void *workspace, size_t workspace_bytes, void *stream) {
+    Geo g;
+    int s = make_geo(p, g);
+    if (s) return s;
+    if (!V || !R || !H || !neg || !pos) return TNMF_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t esz = p->dtype == TNMF_F32 ? 4 : 8;
+    const size_t count = (size_t)g.M * g.C * (size_t)vol3(g.A);
+    if (g.N == 0) {
+        cudaError_t e = cudaMemsetAsync(neg, 0, count * esz, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(pos, 0, count * esz, st);
+        return status_from_cuda(e);
+    }
+    const bool tiled = use_tiled(p, g, &s);
+    if (s) return s;
+    if (tiled) {
+        if (!workspace || workspace_bytes < tnmf_workspace_bytes(p)) return TNMF_EWORKSPACE;
+        return tiled_gradient_w(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,
+                                workspace, workspace_bytes, st);
+    }
+    if (p->dtype == TNMF_F32)
+        return generic_gradient_w<float>(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg,
+                                         (float *)pos, st);
+    return generic_gradient_w<double>(g, (const double *)V, (const double *)R, (const double *)H, (double *)neg,
+                                      (double *)pos, st);
+}
+
+int tnmf_update_w(const tnmf_problem *p, void *W, const void *neg, const void *pos, double eps, void *stream) {
+    Geo g;
+    int s = make_geo(p, g);
+    if (s) return s;
+    if (!W || !neg || !pos) return TNMF_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->dtype == TNMF_F32) return update_w<float>(g, (float *)W, (const float *)neg, (const float *)pos, eps, st);
+    return update_w<double>(g, (double *)W, (const double *)neg, (const double *)pos, eps, st);
+}
+
+int tnmf_normalize(int32_t dtype, void *arr, int64_t outer, int64_t len, int64_t inner, void *stream) {
+    if (!arr || outer < 1 || len < 1 || inner < 1) return TNMF_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TNMF_F32) return normalize_axis<float>((float *)arr, outer, len, inner, st);
+    if (dtype == TNMF_F64) return normalize_axis<double>((double *)arr, outer, len, inner, st);
+    return TNMF_EUNSUPPORTED;
+}
+
+int tnmf_convolve_1d(int32_t dtype, const void *in, void *out, int64_t outer, int64_t len, int64_t inner,
+                     const double *taps, int32_t n_taps, void *stream) {
+    if (!in || !out || in == out || !taps || outer < 0 || len < 1 || inner < 1) return TNMF_EINVAL;
+    if (outer == 0) return TNMF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TNMF_F32)
+        return convolve_axis<float>((const float *)in, (float *)out, outer, len, inner, taps, n_taps, st);
+    if (dtype == TNMF_F64)
+        return convolve_axis<double>((const double *)in, (double *)out, outer, len, inner, taps, n_taps, st);
+    return TNMF_EUNSUPPORTED;
+}
+
+int tnmf_sum_atoms(int32_t dtype, const void *G, void *Gsum, int64_t n_samples, int64_t n_atoms, int64_t inner,
+                   void *stream) {
+    if (!G || !Gsum || n_samples < 0 || n_atoms < 1 || inner < 1) return TNMF_EINVAL;
+    if (n_samples == 0) return TNMF_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == TNMF_F32) return sum_atoms<float>((const float *)G, (float *)Gsum, n_samples, n_atoms, inner, st);
+    if (dtype == TNMF_F64) return sum_atoms<double>((const double *)G, (double *)Gsum, n_samples, n_atoms, inner, st);
+    return TNMF_EUNSUPPORTED;
+}
+
+int tnmf_fp32_peak_probe(void *sink, int32_t iterations, double *flops_out, void *stream) {
+    if (!sink || iterations < 1) return TNMF_EINVAL;
+    return fp32_peak_probe(sink, iterations, flops_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+// Shared definitions of the tnmf_b200 kernels (sm_100a).
+//
+// Internally every problem is three-dimensional (z, y, x); lower ranks get leading extents of 1.  The three
+// reconstruction modes of the reference (tnmf/backends/_Backend.py:60-73, _PyTorchBackend.py:42-52) differ
+// only in an index offset and a boundary rule, so one set of kernels serves all of them:
+//
+//   R[d]      = sum_a W[a] * Hext[d + off - a]          Hext: H on [0,T), else 0 ('wrap': periodic)
+//   gradH[t]  = sum_a W[a] * Xext[t - off + a]          Xext: X on [0,D), else 0 ('wrap': periodic)
+//   gradW[a]  = sum_d Hext[d + off - a] * X[d]
+//
+//   valid: off = A-1, T = D+A-1 (boundary rule never triggers for H)
+//   full:  off = 0,   T = D-A+1 (zero rule for H, never triggers for X)
+//   circular: off = 0, T = D, wrap
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/tnmf_b200.h"
+
+namespace tnmf {
+
+struct Geo {
+    int N, C, M;
+    int D[3];      // sample extent  (z, y, x)
+    int A[3];      // atom extent
+    int T[3];      // activation extent
+    int off[3];    // A-1 for 'valid', 0 otherwise
+    int wrap;      // 1 for 'circular'
+    int ndim;
+    long long hsn, hsm;   // element strides of H's leading axes
+};
+
+__host__ __device__ inline long long vol3(const int *s) { return (long long)s[0] * s[1] * s[2]; }
+
+// Map a logical index onto [0, extent): returns false when the element is an implicit zero.
+__device__ __forceinline__ bool fold_index(int &i, int extent, int wrap) {
+    if (wrap) {
+        i %= extent;
+        if (i < 0) i += extent;
+        return true;
+    }
+    return (unsigned)i < (unsigned)extent;
+}
+
+inline int status_from_cuda(cudaError_t e) { return e == cudaSuccess ? TNMF_OK : TNMF_ECUDA + (int)e; }
+
+#define TNMF_CHECK_LAUNCH()                                        \
+    do {                                                           \
+        cudaError_t e__ = cudaGetLastError();                      \
+        if (e__ != cudaSuccess) return status_from_cuda(e__);      \
+    } while (0)
+
+// ---- implemented in generic_kernels.cu -----------------------------------------------------------------
+template <typename T> int generic_reconstruct(const Geo &g, const T *W, const T *H, T *R, const T *V,
+                                              double *energy_partials, int *n_partials, cudaStream_t st);
+template <typename T> int generic_gradient_h(const Geo &g, const T *V, const T *R, const T *W, T *neg, T *pos,
+                                             T *H, double reg, const T *G, double lambda, const T *Gsum,
+                                             double lambda_cross, cudaStream_t st);
+template <typename T> int generic_gradient_w(const Geo &g, const T *V, const T *R, const T *H, T *neg, T *pos,
+                                             cudaStream_t st);
+int generic_energy_partial_capacity(const Geo &g);
+
+// ---- implemented in tiled_kernels.cu --------------------------------------------------------------------
+bool tiled_supported(const Geo &g, int dtype);
+size_t tiled_workspace_bytes(const Geo &g);
+int tiled_reconstruct(const Geo &g, const float *W, const float *H, float *R, const float *V,
+                      double *energy_partials, int *n_partials, cudaStream_t st);
+int tiled_gradient_h(const Geo &g, const float *V, const float *R, const float *W, float *neg, float *pos,
+                     float *H, double reg, const float *G, double lambda, const float *Gsum,
+                     double lambda_cross, cudaStream_t st);
+int tiled_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos,
+                     void *workspace, size_t workspace_bytes, cudaStream_t st);
+
+// ---- implemented in elementwise.cu ----------------------------------------------------------------------
+int finish_energy(const double *partials, int n, double *energy, cudaStream_t st);
+template <typename T> int finish_gradient_w(const T *partials, int n_partials, long long count, T *neg, T *pos,
+                                            cudaStream_t st);
+template <typename T> int update_w(const Geo &g, T *W, const T *neg, const T *pos, double eps, cudaStream_t st);
+template <typename T> int normalize_axis(T *arr, long long outer, long long len, long long inner, cudaStream_t st);
+template <typename T> int convolve_axis(const T *in, T *out, long long outer, long long len, long long inner,
+                                        const double *taps, int n_taps, cudaStream_t st);
+template <typename T> int sum_atoms(const T *G, T *Gsum, long long n, long long m, long long inner, cudaStream_t st);
+int fp32_peak_probe(void *sink, int iterations, double *flops_out, cudaStream_t st);
+
+}  // namespace tnmf
