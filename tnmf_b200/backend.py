@@ -16,6 +16,7 @@ Two groups of methods:
     (tnmf/TransformInvariantNMF.py:217-271) into the kernels' epilogues.
 """
 import ctypes
+from contextlib import contextmanager
 from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -74,10 +75,24 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self._problems = {}
         self._taps = {}
         self.launches = 0       # number of kernels of this library launched so far (bench.py reports it)
+        self.kernel_events = None   # set to {} to record a (start, end) CUDA-event pair around every hot-path call
 
     # -----------------------------------------------------------------------------------------------
     # plumbing
     # -----------------------------------------------------------------------------------------------
+    @contextmanager
+    def _timed(self, name: str):
+        """CUDA events on the launching stream around one C-ABI call (only while `kernel_events` is a dict)."""
+        if self.kernel_events is None:
+            yield
+            return
+        st = torch.cuda.current_stream(self.device)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        yield
+        b.record(st)
+        self.kernel_events.setdefault(name, []).append((a, b))
+
     def _to_device(self, arr, dtype=None) -> torch.Tensor:
         if isinstance(arr, torch.Tensor):
             t = arr
@@ -269,8 +284,9 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         W = W if W.is_contiguous() else W.contiguous()
         R = out if out is not None else torch.empty((H.shape[0], self.n_channels, *self._sample_shape),
                                                     dtype=self._dtype, device=self.device)
-        _lib.check(self._lib.tnmf_reconstruct(ctypes.byref(p), W.data_ptr(), H.data_ptr(), R.data_ptr(),
-                                              _stream_ptr(self.device)), 'reconstruct')
+        with self._timed('reconstruct'):
+            _lib.check(self._lib.tnmf_reconstruct(ctypes.byref(p), W.data_ptr(), H.data_ptr(), R.data_ptr(),
+                                                  _stream_ptr(self.device)), 'reconstruct')
         self.launches += 1
         return R
 
@@ -362,8 +378,10 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
                 Gsum_ptr = Gsum.data_ptr()
                 lam_cross = float(cross_inhibition) / (self.n_atoms - 1)
         reg = eps + sparsity if sparsity > 0 else eps
-        _lib.check(self._lib.tnmf_update_h(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), W.data_ptr(), Hs.data_ptr(),
-                                           float(reg), G_ptr, lam, Gsum_ptr, lam_cross, st), 'update_h')
+        with self._timed('update_h'):
+            _lib.check(self._lib.tnmf_update_h(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), W.data_ptr(),
+                                               Hs.data_ptr(), float(reg), G_ptr, lam, Gsum_ptr, lam_cross, st),
+                       'update_h')
         self.launches += 1
 
     def gradient_W(self, V, W, H, s: slice, out: torch.Tensor) -> torch.Tensor:
@@ -377,9 +395,10 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             return out
         R = self.reconstruct(W, Hs, out=self._R_for(n))
         ws, ws_bytes = self._workspace(p)
-        _lib.check(self._lib.tnmf_gradient_w(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), Hs.data_ptr(),
-                                             out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws_bytes,
-                                             _stream_ptr(self.device)), 'gradient_w')
+        with self._timed('gradient_w'):
+            _lib.check(self._lib.tnmf_gradient_w(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), Hs.data_ptr(),
+                                                 out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws_bytes,
+                                                 _stream_ptr(self.device)), 'gradient_w')
         self.launches += 2
         return out
 
@@ -387,6 +406,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         """W <- (W*neg)/(pos+eps), then per-(atom, channel) normalisation, in place
         (tnmf/TransformInvariantNMF.py:217-244, tnmf/backends/_Backend.py:75-77).  grad = stacked (neg, pos)."""
         p = self._problem(0, self.n_atoms)
-        _lib.check(self._lib.tnmf_update_w(ctypes.byref(p), W.data_ptr(), grad[0].data_ptr(), grad[1].data_ptr(),
-                                           float(eps), _stream_ptr(self.device)), 'update_w')
+        with self._timed('update_w'):
+            _lib.check(self._lib.tnmf_update_w(ctypes.byref(p), W.data_ptr(), grad[0].data_ptr(), grad[1].data_ptr(),
+                                               float(eps), _stream_ptr(self.device)), 'update_w')
         self.launches += 1
