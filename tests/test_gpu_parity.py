@@ -338,7 +338,8 @@ def test_trilinear_identities_at_full_size(name):
     H2 = torch.rand_like(H)
     R2 = be.reconstruct(W, H2).clone()
     R12 = be.reconstruct(W, H + 2 * H2)
-    _close(R12, (R + 2 * R2).cpu().numpy(), 1e-5)
+    # float32 chains of K = M*prod(A) terms (32768 at cfg5): rounding grows like sqrt(K)*2^-24
+    _close(R12, (R + 2 * R2).cpu().numpy(), 5e-5)
     # energy = 0.5*||V - R||^2
     e = be.reconstruction_energy(V, W, H)
     assert np.isclose(e, 0.5 * float(((V.double() - R.double()) ** 2).sum()), rtol=1e-6)

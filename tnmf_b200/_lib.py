@@ -15,7 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libtnmf_b200.so')
 SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu')
-HEADERS = ('common.cuh', os.path.join('..', '..', 'include', 'tnmf_b200.h'))
+# compiled once per atom-width chunk (-DTNMF_AXC=...): the register-tiled kernels
+CHUNKED_SOURCES = ('tiled_recon.cu', 'tiled_hupd.cu', 'tiled_gradw.cu')
+CHUNKS = (4, 8, 12, 16)
+HEADERS = ('common.cuh', 'tiled_common.cuh', os.path.join('..', '..', 'include', 'tnmf_b200.h'))
 
 # NB: no --use_fast_math: divisions must round like the reference's IEEE arithmetic.
 NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -66,32 +69,41 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + CHUNKED_SOURCES]
+    deps += [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS] + [os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, jobs: Optional[int] = None) -> str:
     """Compile the CUDA sources for sm_100a into tnmf_b200/libtnmf_b200.so (in-tree, travels with the repo)."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libtnmf_b200.so')
-    objs = []
-    procs = []
-    os.makedirs(os.path.join(HERE, '_obj'), exist_ok=True)
-    for s in SOURCES:
-        obj = os.path.join(HERE, '_obj', s.replace('.cu', '.o'))
-        objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, '-Xptxas', '-v', '-c', os.path.join(CSRC, s), '-o', obj]
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    log = []
-    for s, pr in procs:
+    objdir = os.path.join(HERE, '_obj')
+    os.makedirs(objdir, exist_ok=True)
+    units = [(s, s.replace('.cu', '.o'), []) for s in SOURCES]
+    units += [(s, s.replace('.cu', f'_axc{c}.o'), [f'-DTNMF_AXC={c}']) for s in CHUNKED_SOURCES for c in CHUNKS]
+    jobs = jobs or max(1, min(len(units), os.cpu_count() or 1))
+    pending = list(units)
+    running, objs, log = [], [], []
+    while pending or running:
+        while pending and len(running) < jobs:
+            src, obj, defs = pending.pop(0)
+            obj = os.path.join(objdir, obj)
+            objs.append(obj)
+            cmd = [nvcc, *NVCC_FLAGS, *defs, '-Xptxas', '-v', '-c', os.path.join(CSRC, src), '-o', obj]
+            running.append((f'{src} {" ".join(defs)}',
+                            subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        name, pr = running.pop(0)
         out, _ = pr.communicate()
-        log.append(f'== {s}\n{out}')
+        log.append(f'== {name}\n{out}')
         if pr.returncode != 0:
-            raise RuntimeError(f'nvcc failed on {s}:\n{out}')
-    with open(os.path.join(HERE, '_obj', 'ptxas.log'), 'w') as f:
+            for _, other in running:
+                other.kill()
+            raise RuntimeError(f'nvcc failed on {name}:\n{out}')
+    with open(os.path.join(objdir, 'ptxas.log'), 'w') as f:
         f.write('\n'.join(log))
     if verbose:
         print('\n'.join(log))

@@ -1,17 +1,22 @@
 // Shared pieces of the register-tiled FP32-FMA kernels (rank <= 2, float).
 //
-// Data movement: global -> shared with cp.async (LDGSTS, 4-byte granules because the halo origin of a tile is
-// not 16-byte aligned in general), zero-filled or wrapped at the borders according to the reconstruction mode,
-// so the compute loops never test a boundary.  Shared -> registers with 16-byte LDS on an XOR-swizzled row
-// layout that is conflict-free for "8 consecutive lanes read 16 bytes at a 32-byte pitch".
+// All three correlations of the iteration are evaluated in "window" form: a thread owns 8 consecutive
+// positions along the fastest axis, keeps a register window of 8+AXC source values and applies AXC taps to
+// it (AXC = atom-width chunk: 4, 8, 12 or 16), so one 16-byte shared-memory load feeds 8..32 FFMAs.
+//
+// Data movement: global -> shared with cp.async (LDGSTS), zero-filled or wrapped at the borders according to
+// the reconstruction mode, so the compute loops never test a boundary.  Shared -> registers with 16-byte LDS on
+// an XOR-swizzled layout (swz below) that is conflict-free for every lane arrangement the planners use:
+// a quarter-warp (the unit a 16-byte LDS is served in) covers R = 1, 2, 4 or 8 consecutive tile rows with 8/R
+// lanes per row at a 32-byte pitch.
 #pragma once
 #include "common.cuh"
 
 namespace tnmf {
 namespace tiled {
 
-constexpr int kCols = 8;          // consecutive output columns per thread
-constexpr int kMaxSmem = 200 * 1024;
+constexpr int kCols = 8;                // consecutive output positions per thread
+constexpr int kMaxSmem = 220 * 1024;    // of the 227 KB a CTA may use on sm_100
 
 // Two-dimensional view of a problem (rank-1 problems have DY = AY = TY = 1).
 struct Geo2 {
@@ -19,24 +24,34 @@ struct Geo2 {
     int DY, DX, AY, AX, TY, TX;
     int offy, offx, wrap;
     long long hsn, hsm;
-    int AXC;      // atom-width chunk handled per register window (4, 8, 12 or 16)
-    int NK;       // number of chunks
-    int AXP;      // padded atom width = NK * AXC
+};
+
+// Atom-width chunking: the atom row is cut into NK chunks of AXC taps (zero-padded to AXP = NK*AXC).
+// drop = 1 when a single chunk carries exactly one dead tap, which the kernels then skip at compile time
+// (odd atom widths 3, 7, 11, 15 cost no padding).
+struct Chunking {
+    int AXC, NK, AXP, drop;
 };
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// atom-width chunk: trade padded (wasted) taps against the shared-memory loads a narrow register window costs
-inline void choose_chunk(int AX, int &AXC, int &NK) {
+inline Chunking choose_chunk(int AX) {
     int best = 4;
     double best_cost = 1e30;
     for (int c = 4; c <= 16; c += 4) {
         const int pad = round_up(AX, c);
-        const double cost = pad * (1.0 + 0.1 * (8.0 + c) / c);
+        const int nk = pad / c;
+        const int eff = (nk == 1 && pad - AX == 1) ? AX : pad;
+        const double cost = eff * (1.0 + 0.1 * (8.0 + c) / c);
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
-    AXC = best;
-    NK = round_up(AX, best) / best;
+    Chunking ch;
+    ch.AXC = best;
+    ch.AXP = round_up(AX, best);
+    ch.NK = ch.AXP / best;
+    ch.drop = (ch.NK == 1 && ch.AXP - AX == 1) ? 1 : 0;
+    return ch;
 }
 
 inline Geo2 make_geo2(const Geo &g) {
@@ -45,20 +60,39 @@ inline Geo2 make_geo2(const Geo &g) {
     q.DY = g.D[1]; q.DX = g.D[2]; q.AY = g.A[1]; q.AX = g.A[2]; q.TY = g.T[1]; q.TX = g.T[2];
     q.offy = g.off[1]; q.offx = g.off[2]; q.wrap = g.wrap;
     q.hsn = g.hsn; q.hsm = g.hsm;
-    choose_chunk(q.AX, q.AXC, q.NK);
-    q.AXP = q.AXC * q.NK;
     return q;
+}
+
+// Lane arrangement of a warp over a 2-D output: LX lanes along x (8 columns each), 32/LX lanes along y.
+// Chooses the power of two that wastes the fewest lanes on the given extent.
+inline int choose_lx(int EY, int EX, int min_lx) {
+    int best = 32;
+    double best_cost = 1e30;
+    for (int lx = 32; lx >= min_lx; lx >>= 1) {
+        const int ly = 32 / lx;
+        const double cost = (double)round_up(EX, kCols * lx) * (double)round_up(EY, ly);
+        if (cost < best_cost * 0.999) { best_cost = cost; best = lx; }
+    }
+    return best;
 }
 
 // ---- device helpers -----------------------------------------------------------------------------------
 
-// element index within a row -> swizzled element index (16-byte units, unit ^= bit 3 of the unit index)
-__device__ __forceinline__ int swz(int e) { return e ^ (((e >> 5) & 1) << 2); }
+// Swizzle of a tile whose row pitch is a multiple of 32 floats: the 16-byte unit index within a 128-byte line
+// is XORed with the line parity (bit 0) and a bit-permuted row index, so that the units {c + 2*lx} of the lanes
+// of a quarter-warp never share a bank group, whatever the row alignment.
+__device__ __forceinline__ int swz_row(int row) { return ((row & 1) | ((row & 2) << 1) | ((row & 4) >> 1)) << 2; }
+__device__ __forceinline__ int swz(int e, int rowbits) { return e ^ ((((e >> 5) & 1) << 2) ^ rowbits); }
 
 __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gmem_src, bool valid) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     const int bytes = valid ? 4 : 0;                       // src-size 0: the 4 destination bytes are zero-filled
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gmem_src, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
@@ -68,28 +102,40 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 // fold a logical row/column index into [0, extent); false = implicit zero
 __device__ __forceinline__ bool fold(int &i, int extent, int wrap) {
     if (wrap) {
-        if (i < 0) i += extent * ((-i + extent - 1) / extent);
-        else if (i >= extent) i %= extent;
+        i %= extent;
+        if (i < 0) i += extent;
         return true;
     }
     return (unsigned)i < (unsigned)extent;
 }
 
 // Stage a [rows x cols] window of a row-major [extent_y x extent_x] plane whose top-left logical coordinate is
-// (gy0, gx0) into shared memory (row pitch `pitch` floats, swizzled when SWZ).  All threads of the block call.
-template <bool SWZ>
-__device__ __forceinline__ void stage_plane(float *dst, int pitch, const float *plane, int extent_y, int extent_x,
-                                            int gy0, int gx0, int rows, int cols, int wrap, int warp, int n_warps,
-                                            int lane) {
+// (gy0, gx0) into a swizzled shared-memory tile (row pitch `pitch` floats, a multiple of 32).  Rows are dealt to
+// warps, columns to lanes.  All threads of the block call.
+__device__ __forceinline__ void stage_plane(float *dst, int pitch, const float *__restrict__ plane, int extent_y,
+                                            int extent_x, int gy0, int gx0, int rows, int cols, int wrap, int warp,
+                                            int n_warps, int lane) {
     for (int r = warp; r < rows; r += n_warps) {
         int y = gy0 + r;
         const bool row_ok = fold(y, extent_y, wrap);
         const float *src_row = plane + (long long)(row_ok ? y : 0) * extent_x;
         float *dst_row = dst + r * pitch;
-        for (int c = lane; c < cols; c += 32) {
-            int x = gx0 + c;
-            const bool ok = fold(x, extent_x, wrap) && row_ok;
-            cp_async4(dst_row + (SWZ ? swz(c) : c), src_row + (ok ? x : 0), ok);
+        const int rb = swz_row(r);
+        if (!wrap) {
+            for (int c = lane; c < cols; c += 32) {
+                const int x = gx0 + c;
+                const bool ok = row_ok && (unsigned)x < (unsigned)extent_x;
+                cp_async4(dst_row + swz(c, rb), src_row + (ok ? x : 0), ok);
+            }
+        } else {
+            int x = (gx0 + lane) % extent_x;
+            if (x < 0) x += extent_x;
+            const int step = 32 % extent_x;
+            for (int c = lane; c < cols; c += 32) {
+                cp_async4(dst_row + swz(c, rb), src_row + x, true);
+                x += step;
+                if (x >= extent_x) x -= extent_x;
+            }
         }
     }
 }
@@ -108,20 +154,62 @@ __device__ __forceinline__ double block_sum(double v, double *red) {
     return v;
 }
 
-// ---- per-operation planners and launchers (one translation unit each) ----------------------------------
-bool recon_plan_ok(const Geo2 &g);
-int recon_launch(const Geo2 &g, const float *W, const float *H, float *R, const float *V, double *energy_partials,
-                 int *n_partials, cudaStream_t st);
-long long recon_grid(const Geo2 &g);
+// ---- launch plans (tiled_kernels.cu) ----------------------------------------------------------------------
 
-bool hupd_plan_ok(const Geo2 &g);
-int hupd_launch(const Geo2 &g, const float *V, const float *R, const float *W, float *neg, float *pos, float *H,
-                float reg, const float *G, float lambda, const float *Gsum, float lambda_cross, cudaStream_t st);
+// Tile geometry shared by the reconstruction and the H-update kernels: a CTA of WX x WY warps, a warp of
+// LX x LY lanes, a thread of RB rows x 8 columns (x CB channels / MB atoms).
+struct TilePlan {
+    Chunking ch;
+    int LX, LY, WX, WY, RB;
+    int NB;              // CB (reconstruction: channels per thread) or MB (H update: atoms per thread)
+    int nblk;            // number of channel / atom blocks
+    int tile_y, tile_x, tiles_y, tiles_x;
+    int HR, WT, pitch;   // staged source rows / columns / row pitch (floats, multiple of 32)
+    int plane_floats, taps_floats, stage_floats, n_stages;
+    int threads;
+    size_t smem;
+    long long grid;
+};
 
-bool gradw_plan_ok(const Geo2 &g);
-size_t gradw_workspace_bytes(const Geo2 &g);
-int gradw_launch(const Geo2 &g, const float *V, const float *R, const float *H, float *neg, float *pos,
-                 void *workspace, size_t workspace_bytes, cudaStream_t st);
+bool make_recon_plan(const Geo2 &g, TilePlan &p);
+bool make_hupd_plan(const Geo2 &g, TilePlan &p);
+
+// W gradient: the flattened (group, work item) space, group = (atom, channel block, tap-unit group), item =
+// (sample, row chunk, column chunk), is dealt to `grid` CTAs in contiguous ranges of `chunk` positions.
+struct GradWPlan {
+    Chunking ch;
+    int CB, ncb;         // channels per thread, channel blocks
+    int BYB;             // tap units (atom row x atom-column chunk) per warp
+    int units;           // AY * NK tap units in total
+    int warps, ugroups;  // warps per CTA, tap-unit groups
+    int LX, LY;          // lane arrangement over a work item
+    int RY, XC;          // rows / columns per work item
+    int ny, nx;          // work items per sample along y / x
+    int pitch_h, pitch_x;
+    int x_floats, h_floats, stage_floats;
+    int threads;
+    size_t smem;
+    int grid;
+    int groups;          // M * ncb * ugroups
+    long long items;     // N * ny * nx
+    long long chunk;     // positions per CTA
+    int smax;            // partial slices per output element (CTAs that can share a group)
+};
+
+bool make_gradw_plan(const Geo2 &g, GradWPlan &p);
+
+// ---- launchers: tiled_recon.cu, tiled_hupd.cu and tiled_gradw.cu are compiled once per atom-width chunk
+// (-DTNMF_AXC=4|8|12|16) and each defines the specialisation of its *_launch_axc template for that chunk.
+template <int AXC>
+int recon_launch_axc(const Geo2 &g, const TilePlan &p, const float *W, const float *H, float *R, const float *V,
+                     double *epart, cudaStream_t st);
+template <int AXC>
+int hupd_launch_axc(const Geo2 &g, const TilePlan &p, const float *V, const float *R, const float *W, float *neg,
+                    float *pos, float *H, float reg, const float *G, float lambda, const float *Gsum,
+                    float lambda_cross, cudaStream_t st);
+template <int AXC>
+int gradw_launch_axc(const Geo2 &g, const GradWPlan &p, const float *V, const float *R, const float *H,
+                     float *partials, cudaStream_t st);
 
 }  // namespace tiled
 }  // namespace tnmf

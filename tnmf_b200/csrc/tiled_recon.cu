@@ -6,40 +6,38 @@
 // cp.async pipeline: stage = H[n,m] tile with halo + the flipped, zero-padded atom slice.  A thread owns RB
 // consecutive rows x 8 consecutive columns x CB channels of accumulators; per H-tile row it loads a register
 // window of 8+AXC values (LDS.128, swizzled, conflict-free) and applies AXC taps x RB rows x CB channels of FFMAs,
-// with the taps arriving as warp-uniform (broadcast) LDS.128.  Bound: FP32 FMA pipe; shared-memory wavefronts are
-// ~30-45 % of the FMA cycles.
+// with the taps arriving as warp-uniform (broadcast) LDS.128.  Bound: FP32 FMA pipe.
+//
+// Compiled once per atom-width chunk: -DTNMF_AXC=4|8|12|16.
 #include "tiled_common.cuh"
+
+#ifndef TNMF_AXC
+#error "compile with -DTNMF_AXC=4|8|12|16"
+#endif
 
 namespace tnmf {
 namespace tiled {
 
-struct ReconPlan {
-    int LX, LY, WX, WY, RB, CB, ncb;
-    int tile_y, tile_x, tiles_y, tiles_x;
-    int HR, WT, pitch, stage_floats;
-    int threads;
-    size_t smem;
-    long long grid;
-};
-
-template <int AXC, int CB, int RB>
-__global__ void __launch_bounds__(256)
-recon_kernel(const Geo2 g, const ReconPlan p, const float *__restrict__ W, const float *__restrict__ H,
+template <int AXC, int DROP, int CB, int RB>
+__global__ void __launch_bounds__(256, 2)
+recon_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ W, const float *__restrict__ H,
              float *__restrict__ R, const float *__restrict__ V, double *__restrict__ epart) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     __shared__ double red[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n_warps = blockDim.x >> 5;
+    const int NK = p.ch.NK, AXP = p.ch.AXP;
 
     long long b = blockIdx.x;
     const int tx_i = (int)(b % p.tiles_x); b /= p.tiles_x;
     const int ty_i = (int)(b % p.tiles_y); b /= p.tiles_y;
-    const int cb = (int)(b % p.ncb);
-    const int n = (int)(b / p.ncb);
+    const int cb = (int)(b % p.nblk);
+    const int n = (int)(b / p.nblk);
     const int x0 = tx_i * p.tile_x, y0 = ty_i * p.tile_y, c0 = cb * CB;
     const int wy = warp / p.WX, wx = warp % p.WX, ly = lane / p.LX, lx = lane % p.LX;
     const int ry0 = (wy * p.LY + ly) * RB, rx0 = (wx * p.LX + lx) * kCols;
-    const int gy0 = y0 + g.offy - (g.AY - 1), gx0 = x0 + g.offx - (g.AXP - 1);
-    const int qpr = g.AXP >> 2;                     // tap quads per atom row
+    const int gy0 = y0 + g.offy - (g.AY - 1), gx0 = x0 + g.offx - (AXP - 1);
+    const bool warp_active = (y0 + wy * p.LY * RB < g.DY) && (x0 + wx * p.LX * kCols < g.DX);
+    constexpr int QC = AXC / 4;                      // tap quads per chunk
 
     float acc[RB][CB][kCols];
 #pragma unroll
@@ -51,19 +49,19 @@ recon_kernel(const Geo2 g, const ReconPlan p, const float *__restrict__ W, const
 
     auto issue = [&](int stage, int m) {
         float *tile = smem + stage * p.stage_floats;
-        float *wf = tile + p.HR * p.pitch;
-        stage_plane<true>(tile, p.pitch, H + n * g.hsn + m * g.hsm, g.TY, g.TX, gy0, gx0, p.HR, p.WT, g.wrap, warp,
-                          n_warps, lane);
+        float *wf = tile + p.plane_floats;
+        stage_plane(tile, p.pitch, H + n * g.hsn + m * g.hsm, g.TY, g.TX, gy0, gx0, p.HR, p.WT, g.wrap, warp,
+                    n_warps, lane);
         // flipped, zero-padded atom slice: wf[by][bx/4][c][bx%4] = W[m][c0+c][AY-1-by][AXP-1-bx]
-        const int total = g.AY * g.AXP * CB;
+        const int total = g.AY * AXP * CB;
         for (int i = tid; i < total; i += blockDim.x) {
             const int c = i % CB;
             const int t = i / CB;
-            const int bx = t % g.AXP, by = t / g.AXP;
-            const int ax = g.AXP - 1 - bx, ay = g.AY - 1 - by;
+            const int bx = t % AXP, by = t / AXP;
+            const int ax = AXP - 1 - bx, ay = g.AY - 1 - by;
             const bool ok = ax < g.AX && (c0 + c) < g.C;
             const float *src = W + (((long long)m * g.C + (ok ? c0 + c : 0)) * g.AY + ay) * g.AX + (ok ? ax : 0);
-            cp_async4(wf + ((by * qpr + (bx >> 2)) * CB + c) * 4 + (bx & 3), src, ok);
+            cp_async4(wf + ((by * (AXP >> 2) + (bx >> 2)) * CB + c) * 4 + (bx & 3), src, ok);
         }
         cp_async_commit();
     };
@@ -77,36 +75,40 @@ recon_kernel(const Geo2 g, const ReconPlan p, const float *__restrict__ W, const
             cp_async_wait<0>();
         }
         __syncthreads();
-        const float *tile = smem + (m & 1) * p.stage_floats;
-        const float4 *wf = reinterpret_cast<const float4 *>(tile + p.HR * p.pitch);
-        const int rows = g.AY + RB - 1;
-        for (int hrr = 0; hrr < rows; ++hrr) {
-            const float *trow = tile + (ry0 + hrr) * p.pitch;
-            for (int k = 0; k < g.NK; ++k) {
-                float win[kCols + AXC];
+        if (warp_active) {
+            const float *tile = smem + (m & 1) * p.stage_floats;
+            const float4 *wf = reinterpret_cast<const float4 *>(tile + p.plane_floats);
+            const int rows = g.AY + RB - 1;
+            for (int hrr = 0; hrr < rows; ++hrr) {
+                const int row = ry0 + hrr;
+                const int rbits = swz_row(row);
+                const float *trow = tile + row * p.pitch;
+                for (int k = 0; k < NK; ++k) {
+                    float win[kCols + AXC];
 #pragma unroll
-                for (int q = 0; q < (kCols + AXC) / 4; ++q) {
-                    const float4 v = lds128(trow + swz(rx0 + k * AXC + 4 * q));
-                    win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
-                }
+                    for (int q = 0; q < (kCols + AXC) / 4; ++q) {
+                        const float4 v = lds128(trow + swz(rx0 + k * AXC + 4 * q, rbits));
+                        win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
+                    }
 #pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    const int by = hrr - r;
-                    if (by < 0 || by >= g.AY) continue;          // warp-uniform
-                    const float4 *wq = wf + (by * qpr + k * (AXC / 4)) * CB;
+                    for (int r = 0; r < RB; ++r) {
+                        const int by = hrr - r;
+                        if (by < 0 || by >= g.AY) continue;          // warp-uniform
+                        const float4 *wq = wf + (by * NK + k) * QC * CB;
 #pragma unroll
-                    for (int q = 0; q < AXC / 4; ++q) {
+                        for (int q = 0; q < QC; ++q) {
 #pragma unroll
-                        for (int c = 0; c < CB; ++c) {
-                            const float4 w = wq[q * CB + c];
+                            for (int c = 0; c < CB; ++c) {
+                                const float4 w = wq[q * CB + c];
 #pragma unroll
-                            for (int j = 0; j < kCols; ++j) {
-                                float a = acc[r][c][j];
-                                a = fmaf(w.x, win[4 * q + j], a);
-                                a = fmaf(w.y, win[4 * q + 1 + j], a);
-                                a = fmaf(w.z, win[4 * q + 2 + j], a);
-                                a = fmaf(w.w, win[4 * q + 3 + j], a);
-                                acc[r][c][j] = a;
+                                for (int j = 0; j < kCols; ++j) {
+                                    float a = acc[r][c][j];
+                                    if (!(DROP && q == 0)) a = fmaf(w.x, win[4 * q + j], a);   // dead tap bx = 0
+                                    a = fmaf(w.y, win[4 * q + 1 + j], a);
+                                    a = fmaf(w.z, win[4 * q + 2 + j], a);
+                                    a = fmaf(w.w, win[4 * q + 3 + j], a);
+                                    acc[r][c][j] = a;
+                                }
                             }
                         }
                     }
@@ -120,37 +122,41 @@ recon_kernel(const Geo2 g, const ReconPlan p, const float *__restrict__ W, const
     double e_local = 0.0;
     const int x = x0 + rx0;
     const bool vec = (g.DX & 3) == 0 && x + kCols <= g.DX;
+    if (warp_active) {
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-        const int y = y0 + ry0 + r;
-        if (y >= g.DY || x >= g.DX) continue;
+        for (int r = 0; r < RB; ++r) {
+            const int y = y0 + ry0 + r;
+            if (y >= g.DY || x >= g.DX) continue;
 #pragma unroll
-        for (int c = 0; c < CB; ++c) {
-            if (c0 + c >= g.C) continue;
-            const long long base = (((long long)n * g.C + c0 + c) * g.DY + y) * g.DX + x;
-            if (vec) {
-                if (R) {
-                    *reinterpret_cast<float4 *>(R + base) = make_float4(acc[r][c][0], acc[r][c][1], acc[r][c][2], acc[r][c][3]);
-                    *reinterpret_cast<float4 *>(R + base + 4) = make_float4(acc[r][c][4], acc[r][c][5], acc[r][c][6], acc[r][c][7]);
-                }
-                if (V) {
-                    const float4 v0 = *reinterpret_cast<const float4 *>(V + base);
-                    const float4 v1 = *reinterpret_cast<const float4 *>(V + base + 4);
-                    const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            for (int c = 0; c < CB; ++c) {
+                if (c0 + c >= g.C) continue;
+                const long long base = (((long long)n * g.C + c0 + c) * g.DY + y) * g.DX + x;
+                if (vec) {
+                    if (R) {
+                        *reinterpret_cast<float4 *>(R + base) =
+                            make_float4(acc[r][c][0], acc[r][c][1], acc[r][c][2], acc[r][c][3]);
+                        *reinterpret_cast<float4 *>(R + base + 4) =
+                            make_float4(acc[r][c][4], acc[r][c][5], acc[r][c][6], acc[r][c][7]);
+                    }
+                    if (V) {
+                        const float4 v0 = *reinterpret_cast<const float4 *>(V + base);
+                        const float4 v1 = *reinterpret_cast<const float4 *>(V + base + 4);
+                        const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                        for (int j = 0; j < kCols; ++j) {
+                            const double d = (double)vv[j] - (double)acc[r][c][j];
+                            e_local += d * d;
+                        }
+                    }
+                } else {
 #pragma unroll
                     for (int j = 0; j < kCols; ++j) {
-                        const double d = (double)vv[j] - (double)acc[r][c][j];
-                        e_local += d * d;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < kCols; ++j) {
-                    if (x + j < g.DX) {
-                        if (R) R[base + j] = acc[r][c][j];
-                        if (V) {
-                            const double d = (double)V[base + j] - (double)acc[r][c][j];
-                            e_local += d * d;
+                        if (x + j < g.DX) {
+                            if (R) R[base + j] = acc[r][c][j];
+                            if (V) {
+                                const double d = (double)V[base + j] - (double)acc[r][c][j];
+                                e_local += d * d;
+                            }
                         }
                     }
                 }
@@ -163,56 +169,10 @@ recon_kernel(const Geo2 g, const ReconPlan p, const float *__restrict__ W, const
     }
 }
 
-static bool make_plan(const Geo2 &g, ReconPlan &p) {
-    const bool one_d = g.DY == 1 && g.AY == 1;
-    p.CB = g.C <= 4 ? g.C : 4;
-    p.ncb = (g.C + p.CB - 1) / p.CB;
-    if (one_d) {
-        p.LX = 32; p.LY = 1; p.WY = 1; p.RB = 1;
-        p.WX = g.DX > 512 ? 4 : (g.DX > 256 ? 2 : 1);
-    } else {
-        p.LX = 8; p.LY = 4; p.WX = 1; p.WY = 8;
-        // rows per thread: as many as the accumulator budget allows (CB*RB <= 4) without padding DY by > 15 %
-        p.RB = 1;
-        for (int rb = (p.CB == 1 ? 4 : (p.CB == 2 ? 2 : 1)); rb > 1; rb >>= 1) {
-            const int ty = 32 * rb;
-            if (round_up(g.DY, ty) <= g.DY + g.DY * 15 / 100) { p.RB = rb; break; }
-        }
-    }
-    for (;;) {
-        p.threads = 32 * p.WX * p.WY;
-        p.tile_y = p.WY * p.LY * p.RB;
-        p.tile_x = p.WX * p.LX * kCols;
-        p.tiles_y = (g.DY + p.tile_y - 1) / p.tile_y;
-        p.tiles_x = (g.DX + p.tile_x - 1) / p.tile_x;
-        p.HR = p.tile_y + g.AY - 1;
-        p.WT = p.tile_x + g.AXP - 1;
-        p.pitch = round_up(p.tile_x + g.AXP, 8);                 // even number of 16-byte units: swizzle stays in-row
-        p.stage_floats = p.HR * p.pitch + g.AY * g.AXP * p.CB;
-        p.stage_floats = round_up(p.stage_floats, 4);
-        p.smem = (size_t)2 * p.stage_floats * sizeof(float);
-        if (p.smem <= (size_t)kMaxSmem) break;
-        if (p.RB > 1) { p.RB >>= 1; continue; }                  // shrink the tile until two stages fit
-        return false;
-    }
-    p.grid = (long long)p.tiles_x * p.tiles_y * p.ncb * g.N;
-    return p.grid > 0 && p.grid < 0x7fffffffLL;
-}
-
-bool recon_plan_ok(const Geo2 &g) {
-    ReconPlan p;
-    return make_plan(g, p);
-}
-
-long long recon_grid(const Geo2 &g) {
-    ReconPlan p;
-    return make_plan(g, p) ? p.grid : 0;
-}
-
-template <int AXC, int CB, int RB>
-static int launch_one(const Geo2 &g, const ReconPlan &p, const float *W, const float *H, float *R, const float *V,
+template <int AXC, int DROP, int CB, int RB>
+static int launch_one(const Geo2 &g, const TilePlan &p, const float *W, const float *H, float *R, const float *V,
                       double *epart, cudaStream_t st) {
-    auto kern = recon_kernel<AXC, CB, RB>;
+    auto kern = recon_kernel<AXC, DROP, CB, RB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     kern<<<(unsigned)p.grid, p.threads, p.smem, st>>>(g, p, W, H, R, V, epart);
@@ -220,11 +180,13 @@ static int launch_one(const Geo2 &g, const ReconPlan &p, const float *W, const f
     return TNMF_OK;
 }
 
-template <int AXC>
-static int launch_axc(const Geo2 &g, const ReconPlan &p, const float *W, const float *H, float *R, const float *V,
-                      double *epart, cudaStream_t st) {
-#define TNMF_RECON_CASE(cb, rb) \
-    if (p.CB == cb && p.RB == rb) return launch_one<AXC, cb, rb>(g, p, W, H, R, V, epart, st);
+template <>
+int recon_launch_axc<TNMF_AXC>(const Geo2 &g, const TilePlan &p, const float *W, const float *H, float *R,
+                               const float *V, double *epart, cudaStream_t st) {
+#define TNMF_RECON_CASE(cb, rb)                                                                         \
+    if (p.NB == cb && p.RB == rb)                                                                       \
+        return p.ch.drop ? launch_one<TNMF_AXC, 1, cb, rb>(g, p, W, H, R, V, epart, st)                 \
+                         : launch_one<TNMF_AXC, 0, cb, rb>(g, p, W, H, R, V, epart, st);
     TNMF_RECON_CASE(1, 1)
     TNMF_RECON_CASE(1, 2)
     TNMF_RECON_CASE(1, 4)
@@ -234,20 +196,6 @@ static int launch_axc(const Geo2 &g, const ReconPlan &p, const float *W, const f
     TNMF_RECON_CASE(4, 1)
 #undef TNMF_RECON_CASE
     return TNMF_EUNSUPPORTED;
-}
-
-int recon_launch(const Geo2 &g, const float *W, const float *H, float *R, const float *V, double *energy_partials,
-                 int *n_partials, cudaStream_t st) {
-    ReconPlan p;
-    if (!make_plan(g, p)) return TNMF_EUNSUPPORTED;
-    if (n_partials) *n_partials = (int)p.grid;
-    switch (g.AXC) {
-        case 4: return launch_axc<4>(g, p, W, H, R, V, energy_partials, st);
-        case 8: return launch_axc<8>(g, p, W, H, R, V, energy_partials, st);
-        case 12: return launch_axc<12>(g, p, W, H, R, V, energy_partials, st);
-        case 16: return launch_axc<16>(g, p, W, H, R, V, energy_partials, st);
-        default: return TNMF_EUNSUPPORTED;
-    }
 }
 
 }  // namespace tiled
