@@ -109,25 +109,31 @@ __device__ __forceinline__ bool fold(int &i, int extent, int wrap) {
     return (unsigned)i < (unsigned)extent;
 }
 
+__device__ __forceinline__ void cp_async8(float *smem_dst, const float *gmem_src, int bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16n(float *smem_dst, const float *gmem_src, int bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // Stage a [rows x cols] window of a row-major [extent_y x extent_x] plane whose top-left logical coordinate is
 // (gy0, gx0) into a swizzled shared-memory tile (row pitch `pitch` floats, a multiple of 32).  Rows are dealt to
-// warps, columns to lanes.  All threads of the block call.
+// warps, 16-byte units to lanes.  Per row the widest cp.async the alignment of the row start allows is used
+// (16, 8 or 4 bytes); elements outside the plane are zero-filled through the src-size operand ('wrap': folded).
+// All threads of the block call.
 __device__ __forceinline__ void stage_plane(float *dst, int pitch, const float *__restrict__ plane, int extent_y,
                                             int extent_x, int gy0, int gx0, int rows, int cols, int wrap, int warp,
                                             int n_warps, int lane) {
+    const int units = (cols + 3) >> 2;
     for (int r = warp; r < rows; r += n_warps) {
         int y = gy0 + r;
         const bool row_ok = fold(y, extent_y, wrap);
         const float *src_row = plane + (long long)(row_ok ? y : 0) * extent_x;
         float *dst_row = dst + r * pitch;
         const int rb = swz_row(r);
-        if (!wrap) {
-            for (int c = lane; c < cols; c += 32) {
-                const int x = gx0 + c;
-                const bool ok = row_ok && (unsigned)x < (unsigned)extent_x;
-                cp_async4(dst_row + swz(c, rb), src_row + (ok ? x : 0), ok);
-            }
-        } else {
+        if (wrap) {
             int x = (gx0 + lane) % extent_x;
             if (x < 0) x += extent_x;
             const int step = 32 % extent_x;
@@ -135,6 +141,32 @@ __device__ __forceinline__ void stage_plane(float *dst, int pitch, const float *
                 cp_async4(dst_row + swz(c, rb), src_row + x, true);
                 x += step;
                 if (x >= extent_x) x -= extent_x;
+            }
+            continue;
+        }
+        if (!row_ok) {
+            for (int u = lane; u < units; u += 32) cp_async16n(dst_row + swz(4 * u, rb), plane, 0);
+            continue;
+        }
+        const unsigned align = (unsigned)(reinterpret_cast<unsigned long long>(src_row + gx0) & 15ull);   // warp-uniform
+        for (int u = lane; u < units; u += 32) {
+            const int x = gx0 + 4 * u;
+            float *d = dst_row + swz(4 * u, rb);
+            const int n_in = extent_x - x;                   // elements of this unit left of the right border
+            if (x >= 0 && align == 0) {
+                const int bytes = n_in >= 4 ? 16 : (n_in > 0 ? 4 * n_in : 0);
+                cp_async16n(d, bytes ? src_row + x : plane, bytes);
+            } else if (x >= 0 && (align & 7) == 0) {
+                const int b0 = n_in >= 2 ? 8 : (n_in > 0 ? 4 * n_in : 0);
+                const int b1 = n_in >= 4 ? 8 : (n_in > 2 ? 4 * (n_in - 2) : 0);
+                cp_async8(d, b0 ? src_row + x : plane, b0);
+                cp_async8(d + 2, b1 ? src_row + x + 2 : plane, b1);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = (unsigned)(x + e) < (unsigned)extent_x;
+                    cp_async4(d + e, src_row + (ok ? x + e : 0), ok);
+                }
             }
         }
     }

@@ -36,7 +36,7 @@ gradw_kernel(const Geo2 g, const GradWPlan p, const float *__restrict__ V, const
     if (pos0 >= pos1) return;
 
     const int lx = lane % p.LX, ly = lane / p.LX;
-    const int g0y = g.offy - (g.AY - 1), g0x = g.offx - (AXP - 1);
+    const int g0y = g.offy - (g.AY - 1), g0x = g.offx - (g.AX - 1);
     const long long dvol = (long long)g.DY * g.DX;
     const long long count = (long long)g.M * g.C * g.AY * g.AX;
     const bool vec_x = (g.DX & 3) == 0;
@@ -59,15 +59,39 @@ gradw_kernel(const Geo2 g, const GradWPlan p, const float *__restrict__ V, const
         return last / NK;
     };
 
-    auto issue = [&](int stage, long long pos) {
-        const int grp = (int)(pos / p.items);
-        const long long it = pos - (long long)grp * p.items;
-        const int ug = grp % p.ugroups;
-        const int cb = (grp / p.ugroups) % p.ncb;
-        const int m = grp / (p.ugroups * p.ncb);
-        const int xc = (int)(it % p.nx);
-        const int yc = (int)((it / p.nx) % p.ny);
-        const int n = (int)(it / ((long long)p.nx * p.ny));
+    // position in the flattened (group, item) space, advanced without divisions
+    struct Cursor {
+        int grp, m, cb, ug, n, yc, xc;
+    };
+    auto decode = [&](long long pos) {
+        Cursor c;
+        c.grp = (int)(pos / p.items);
+        const long long it = pos - (long long)c.grp * p.items;
+        c.ug = c.grp % p.ugroups;
+        c.cb = (c.grp / p.ugroups) % p.ncb;
+        c.m = c.grp / (p.ugroups * p.ncb);
+        c.xc = (int)(it % p.nx);
+        c.yc = (int)((it / p.nx) % p.ny);
+        c.n = (int)(it / ((long long)p.nx * p.ny));
+        return c;
+    };
+    auto advance = [&](Cursor &c) {
+        if (++c.xc < p.nx) return;
+        c.xc = 0;
+        if (++c.yc < p.ny) return;
+        c.yc = 0;
+        if (++c.n < g.N) return;
+        c.n = 0;
+        ++c.grp;
+        if (++c.ug < p.ugroups) return;
+        c.ug = 0;
+        if (++c.cb < p.ncb) return;
+        c.cb = 0;
+        ++c.m;
+    };
+
+    auto issue = [&](int stage, const Cursor &cur) {
+        const int ug = cur.ug, cb = cur.cb, m = cur.m, xc = cur.xc, yc = cur.yc, n = cur.n;
         float *tx = smem + stage * p.stage_floats;
         float *th = tx + p.x_floats;
         const int y_base = yc * p.RY, x_base = xc * p.XC;
@@ -127,9 +151,9 @@ gradw_kernel(const Geo2 g, const GradWPlan p, const float *__restrict__ V, const
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                         const int flat = ((i * 2 + X) * CB + c) * AXC + bx;
-                        const int ax = AXP - 1 - (k * AXC + bx);
+                        const int ax = g.AX - 1 - (k * AXC + bx);
                         const int ch = cb * CB + c;
-                        if (lane == (flat & 31) && u < p.units && ax < g.AX && ch < g.C) {
+                        if (lane == (flat & 31) && u < p.units && ax >= 0 && ch < g.C) {
                             const int ay = g.AY - 1 - by;
                             slot[X * count + (((long long)m * g.C + ch) * g.AY + ay) * g.AX + ax] = v;
                         }
@@ -137,26 +161,26 @@ gradw_kernel(const Geo2 g, const GradWPlan p, const float *__restrict__ V, const
         }
     };
 
-    issue(0, pos0);
-    int cur_grp = (int)(pos0 / p.items);
+    Cursor cur = decode(pos0), ahead = cur;
+    issue(0, ahead);
+    int cur_grp = cur.grp;
     for (long long pos = pos0; pos < pos1; ++pos) {
         const int stage = (int)((pos - pos0) & 1);
         if (pos + 1 < pos1) {
-            issue(stage ^ 1, pos + 1);
+            advance(ahead);
+            issue(stage ^ 1, ahead);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
         __syncthreads();
-        const int grp = (int)(pos / p.items);
+        if (pos != pos0) advance(cur);
+        const int grp = cur.grp;
         if (grp != cur_grp) {
             flush(cur_grp);
             cur_grp = grp;
         }
-        const long long it = pos - (long long)grp * p.items;
-        const int ug = grp % p.ugroups;
-        const int xc = (int)(it % p.nx);
-        const int yc = (int)((it / p.nx) % p.ny);
+        const int ug = cur.ug, xc = cur.xc, yc = cur.yc;
         const int by_lo = by_lo_of(ug);
         const int ubase = (ug * p.warps + warp) * BYB;
         int by_i[BYB], k_i[BYB];
@@ -202,7 +226,7 @@ gradw_kernel(const Geo2 g, const GradWPlan p, const float *__restrict__ V, const
                                 xv[c][4] = b4.x; xv[c][5] = b4.y; xv[c][6] = b4.z; xv[c][7] = b4.w;
                             }
 #pragma unroll
-                            for (int bx = (DROP ? 1 : 0); bx < AXC; ++bx)
+                            for (int bx = 0; bx < AXC - DROP; ++bx)
 #pragma unroll
                                 for (int j = 0; j < kCols; ++j)
 #pragma unroll
@@ -237,7 +261,7 @@ gradw_kernel(const Geo2 g, const GradWPlan p, const float *__restrict__ V, const
                                 win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
                             }
 #pragma unroll
-                            for (int bx = (DROP ? 1 : 0); bx < AXC; ++bx)
+                            for (int bx = 0; bx < AXC - DROP; ++bx)
 #pragma unroll
                                 for (int j = 0; j < kCols; ++j)
 #pragma unroll

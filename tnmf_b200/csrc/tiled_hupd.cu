@@ -22,7 +22,7 @@ namespace tnmf {
 namespace tiled {
 
 template <int AXC, int DROP, int MB>
-__global__ void __launch_bounds__(256, (MB <= 2) ? 2 : 1)
+__global__ void __launch_bounds__(256, 2)
 hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const float *__restrict__ R,
             const float *__restrict__ W, float *__restrict__ neg_out, float *__restrict__ pos_out,
             float *__restrict__ H, float reg, const float *__restrict__ G, float lambda,
@@ -58,14 +58,21 @@ hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const f
         stage_plane(tv, p.pitch, V + plane, g.DY, g.DX, gy0, gx0, p.HR, p.WT, g.wrap, warp, n_warps, lane);
         stage_plane(tr, p.pitch, R + plane, g.DY, g.DX, gy0, gx0, p.HR, p.WT, g.wrap, warp, n_warps, lane);
         // zero-padded atom slices: wt[ay][ax/4][i][ax%4] = W[m0+i][c][ay][ax]
-        const int total = g.AY * AXP * MB;
-        for (int i = tid; i < total; i += blockDim.x) {
+        const int qpr = AXP >> 2;
+        const int groups = g.AY * qpr * MB;
+        for (int i = tid; i < groups; i += blockDim.x) {
             const int im = i % MB;
             const int t = i / MB;
-            const int ax = t % AXP, ay = t / AXP;
-            const bool ok = ax < g.AX && (m0 + im) < g.M;
-            const float *src = W + (((long long)(ok ? m0 + im : 0) * g.C + c) * g.AY + ay) * g.AX + (ok ? ax : 0);
-            cp_async4(wt + ((ay * (AXP >> 2) + (ax >> 2)) * MB + im) * 4 + (ax & 3), src, ok);
+            const int q = t % qpr, ay = t / qpr;
+            const bool m_ok = (m0 + im) < g.M;
+            const float *wrow = W + (((long long)(m_ok ? m0 + im : 0) * g.C + c) * g.AY + ay) * g.AX;
+            float *d = wt + ((ay * qpr + q) * MB + im) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ax = 4 * q + e;
+                const bool ok = m_ok && ax < g.AX;
+                cp_async4(d + e, wrow + (ok ? ax : 0), ok);
+            }
         }
         cp_async_commit();
     };
@@ -88,31 +95,31 @@ hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const f
                 const int rbits = swz_row(row);
                 const int roff = row * p.pitch;
                 for (int k = 0; k < NK; ++k) {
-                    float wv[kCols + AXC], wr[kCols + AXC];
-#pragma unroll
-                    for (int q = 0; q < (kCols + AXC) / 4; ++q) {
-                        const int e = roff + swz(rx0 + k * AXC + 4 * q, rbits);
-                        const float4 a = lds128(tv + e);
-                        const float4 r4 = lds128(tr + e);
-                        wv[4 * q] = a.x; wv[4 * q + 1] = a.y; wv[4 * q + 2] = a.z; wv[4 * q + 3] = a.w;
-                        wr[4 * q] = r4.x; wr[4 * q + 1] = r4.y; wr[4 * q + 2] = r4.z; wr[4 * q + 3] = r4.w;
-                    }
                     const float4 *wq = wt + (ay * NK + k) * QC * MB;
+                    // the V window feeds neg, then the R window feeds pos: one window live at a time
 #pragma unroll
-                    for (int q = 0; q < QC; ++q) {
+                    for (int X = 0; X < 2; ++X) {
+                        const float *src = X ? tr : tv;
+                        float win[kCols + AXC];
 #pragma unroll
-                        for (int i = 0; i < MB; ++i) {
-                            const float4 w = wq[q * MB + i];
+                        for (int q = 0; q < (kCols + AXC) / 4; ++q) {
+                            const float4 a = lds128(src + roff + swz(rx0 + k * AXC + 4 * q, rbits));
+                            win[4 * q] = a.x; win[4 * q + 1] = a.y; win[4 * q + 2] = a.z; win[4 * q + 3] = a.w;
+                        }
 #pragma unroll
-                            for (int j = 0; j < kCols; ++j) {
-                                float a = neg[i][j], bq = pos[i][j];
-                                a = fmaf(w.x, wv[4 * q + j], a);          bq = fmaf(w.x, wr[4 * q + j], bq);
-                                a = fmaf(w.y, wv[4 * q + 1 + j], a);      bq = fmaf(w.y, wr[4 * q + 1 + j], bq);
-                                a = fmaf(w.z, wv[4 * q + 2 + j], a);      bq = fmaf(w.z, wr[4 * q + 2 + j], bq);
-                                if (!(DROP && q == QC - 1)) {             // dead tap ax = AXP-1
-                                    a = fmaf(w.w, wv[4 * q + 3 + j], a);  bq = fmaf(w.w, wr[4 * q + 3 + j], bq);
+                        for (int q = 0; q < QC; ++q) {
+#pragma unroll
+                            for (int i = 0; i < MB; ++i) {
+                                const float4 w = wq[q * MB + i];
+#pragma unroll
+                                for (int j = 0; j < kCols; ++j) {
+                                    float a = X ? pos[i][j] : neg[i][j];
+                                    a = fmaf(w.x, win[4 * q + j], a);
+                                    a = fmaf(w.y, win[4 * q + 1 + j], a);
+                                    a = fmaf(w.z, win[4 * q + 2 + j], a);
+                                    if (!(DROP && q == QC - 1)) a = fmaf(w.w, win[4 * q + 3 + j], a);   // dead tap
+                                    if (X) pos[i][j] = a; else neg[i][j] = a;
                                 }
-                                neg[i][j] = a; pos[i][j] = bq;
                             }
                         }
                     }
@@ -127,6 +134,15 @@ hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const f
     if (ty >= g.TY || tx >= g.TX) return;
     const long long tvol = (long long)g.TY * g.TX;
     const long long tin = (long long)ty * g.TX + tx;
+    float hv[MB][kCols];
+    if (H) {
+#pragma unroll
+        for (int i = 0; i < MB; ++i) {                               // all H loads in flight before the first use
+            const float *hp = H + n * g.hsn + (m0 + i < g.M ? m0 + i : m0) * g.hsm + tin;
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) hv[i][j] = (tx + j < g.TX) ? hp[j] : 0.f;
+        }
+    }
 #pragma unroll
     for (int i = 0; i < MB; ++i) {
         const int m = m0 + i;
@@ -134,15 +150,21 @@ hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const f
         const long long cidx = ((long long)n * g.M + m) * tvol + tin;        // contiguous [n, m, T] tensors
         if (H) {
             float *hp = H + n * g.hsn + m * g.hsm + tin;
+            float gi[kCols], gs[kCols];
+#pragma unroll
+            for (int j = 0; j < kCols; ++j) {
+                const bool ok = tx + j < g.TX;
+                gi[j] = (ok && G) ? G[cidx + j] : 0.f;
+                gs[j] = (ok && Gsum) ? Gsum[(long long)n * tvol + tin + j] : 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < kCols; ++j) {
                 if (tx + j >= g.TX) continue;
-                const float h = hp[j];
+                const float h = hv[i][j];
                 float ps = pos[i][j];
                 if (G) {
-                    const float gi = G[cidx + j];
-                    if (lambda != 0.f) { float tmp = gi - h; tmp *= lambda; ps += tmp; }
-                    if (Gsum) { float tmp = -gi + Gsum[(long long)n * tvol + tin + j]; tmp *= lambda_cross; ps += tmp; }
+                    if (lambda != 0.f) { float tmp = gi[j] - h; tmp *= lambda; ps += tmp; }
+                    if (Gsum) { float tmp = -gi[j] + gs[j]; tmp *= lambda_cross; ps += tmp; }
                 }
                 ps += reg;
                 float hn = h * neg[i][j];

@@ -35,7 +35,7 @@ recon_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ W, const 
     const int x0 = tx_i * p.tile_x, y0 = ty_i * p.tile_y, c0 = cb * CB;
     const int wy = warp / p.WX, wx = warp % p.WX, ly = lane / p.LX, lx = lane % p.LX;
     const int ry0 = (wy * p.LY + ly) * RB, rx0 = (wx * p.LX + lx) * kCols;
-    const int gy0 = y0 + g.offy - (g.AY - 1), gx0 = x0 + g.offx - (AXP - 1);
+    const int gy0 = y0 + g.offy - (g.AY - 1), gx0 = x0 + g.offx - (g.AX - 1);   // 'valid': the tile origin itself
     const bool warp_active = (y0 + wy * p.LY * RB < g.DY) && (x0 + wx * p.LX * kCols < g.DX);
     constexpr int QC = AXC / 4;                      // tap quads per chunk
 
@@ -52,16 +52,22 @@ recon_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ W, const 
         float *wf = tile + p.plane_floats;
         stage_plane(tile, p.pitch, H + n * g.hsn + m * g.hsm, g.TY, g.TX, gy0, gx0, p.HR, p.WT, g.wrap, warp,
                     n_warps, lane);
-        // flipped, zero-padded atom slice: wf[by][bx/4][c][bx%4] = W[m][c0+c][AY-1-by][AXP-1-bx]
-        const int total = g.AY * AXP * CB;
-        for (int i = tid; i < total; i += blockDim.x) {
+        // flipped atom slice, zero-padded at the end: wf[by][bx/4][c][bx%4] = W[m][c0+c][AY-1-by][AX-1-bx]
+        const int qpr = AXP >> 2;
+        const int groups = g.AY * qpr * CB;
+        for (int i = tid; i < groups; i += blockDim.x) {
             const int c = i % CB;
             const int t = i / CB;
-            const int bx = t % AXP, by = t / AXP;
-            const int ax = AXP - 1 - bx, ay = g.AY - 1 - by;
-            const bool ok = ax < g.AX && (c0 + c) < g.C;
-            const float *src = W + (((long long)m * g.C + (ok ? c0 + c : 0)) * g.AY + ay) * g.AX + (ok ? ax : 0);
-            cp_async4(wf + ((by * (AXP >> 2) + (bx >> 2)) * CB + c) * 4 + (bx & 3), src, ok);
+            const int q = t % qpr, by = t / qpr;
+            const bool c_ok = (c0 + c) < g.C;
+            const float *wrow = W + (((long long)m * g.C + (c_ok ? c0 + c : 0)) * g.AY + (g.AY - 1 - by)) * g.AX;
+            float *d = wf + ((by * qpr + q) * CB + c) * 4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int ax = g.AX - 1 - (4 * q + e);
+                const bool ok = c_ok && ax >= 0;
+                cp_async4(d + e, wrow + (ok ? ax : 0), ok);
+            }
         }
         cp_async_commit();
     };
@@ -103,10 +109,10 @@ recon_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ W, const 
 #pragma unroll
                                 for (int j = 0; j < kCols; ++j) {
                                     float a = acc[r][c][j];
-                                    if (!(DROP && q == 0)) a = fmaf(w.x, win[4 * q + j], a);   // dead tap bx = 0
+                                    a = fmaf(w.x, win[4 * q + j], a);
                                     a = fmaf(w.y, win[4 * q + 1 + j], a);
                                     a = fmaf(w.z, win[4 * q + 2 + j], a);
-                                    a = fmaf(w.w, win[4 * q + 3 + j], a);
+                                    if (!(DROP && q == QC - 1)) a = fmaf(w.w, win[4 * q + 3 + j], a);   // dead last tap
                                     acc[r][c][j] = a;
                                 }
                             }
