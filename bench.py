@@ -329,7 +329,7 @@ def run_b200(args, w):
         'config': {'workload': f'{args.workload}: {w["text"]}', 'algorithm': 'batch MU (H update, W update)',
                    'samples_per_gpu': n_local, 'global_samples': world * n_local,
                    'parallelism': f'sample-sharded x{world}, all-reduce of the W gradient' if world > 1 else 'single GPU',
-                   'kernel_path': 'tiled' if be.uses_tiled_kernels() else 'generic',
+                   'kernel_path': be.kernel_families(),
                    'l2': 'working set (V, R, H) exceeds the 126 MB L2; no explicit flush'
                    if (bytes_step / 5 > 126e6) else 'working set fits L2; iterations overwrite H and R in between',
                    'final_energy': energy},
@@ -351,7 +351,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
-    ap.add_argument('--kernel-path', default='auto', choices=['auto', 'generic', 'tiled'])
+    ap.add_argument('--kernel-path', default='auto', choices=['auto', 'generic', 'tiled', 'tma'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

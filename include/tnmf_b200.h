@@ -16,7 +16,8 @@
  *   - every call is stream-ordered on `stream` (a cudaStream_t passed as void*); nothing synchronises;
  *   - tensors are C-contiguous in the reference's layouts  V,R[n,c,*D]  W[m,c,*A]  H[n,m,*T]  except that H
  *     may carry arbitrary strides on its two leading axes (tnmf/backends/_Backend.py:124-125 passes
- *     H[:, i:i+1]);
+ *     H[:, i:i+1]) and a padded pitch between its rows (the stride of the second-to-last shift axis; the
+ *     TMA kernels need every H stride to be a multiple of 4 elements);
  *   - the element type of all tensors is `dtype` (float or double; "dtype follows V",
  *     tnmf/backends/_Backend.py:92,95);
  *   - return value: 0 on success, a TNMF_E* code otherwise; errors never cross the boundary as exceptions.
@@ -32,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TNMF_ABI_VERSION 1
+#define TNMF_ABI_VERSION 2
 #define TNMF_MAX_SHIFT_DIMS 3
 
 /* element types */
@@ -47,7 +48,13 @@ extern "C" {
 /* kernel family selection (diagnostics / tests); 0 lets the library choose */
 #define TNMF_PATH_AUTO    0
 #define TNMF_PATH_GENERIC 1   /* one-thread-per-output kernels, any rank <= 3, float and double */
-#define TNMF_PATH_TILED   2   /* shared-memory staged register-tiled FP32-FMA kernels (rank <= 2, float) */
+#define TNMF_PATH_TILED   2   /* cp.async-staged register-tiled FP32-FMA kernels (rank <= 2, float, all modes) */
+#define TNMF_PATH_TMA     3   /* persistent warp-specialised TMA + mbarrier kernels (rank 2, float, valid/full) */
+
+/* operations, for tnmf_kernel_family() */
+#define TNMF_OP_RECONSTRUCT 0
+#define TNMF_OP_GRADIENT_H  1   /* also the fused H update */
+#define TNMF_OP_GRADIENT_W  2
 
 /* status codes */
 #define TNMF_OK            0
@@ -66,7 +73,7 @@ typedef struct tnmf_problem {
     int32_t n_samples;                          /* N (of this call: a minibatch passes its own size) */
     int32_t n_channels;                         /* C                                                 */
     int32_t n_atoms;                            /* M                                                 */
-    int32_t reserved;
+    int32_t h_pitch;                            /* element stride between rows of H; 0 = dense (T[-1]) */
     int32_t sample_shape[TNMF_MAX_SHIFT_DIMS];  /* D                                                 */
     int32_t atom_shape[TNMF_MAX_SHIFT_DIMS];    /* A                                                 */
     int64_t h_stride_n;                         /* element strides of H's axes 0 and 1; 0 = contiguous */
@@ -79,16 +86,22 @@ const char *tnmf_status_string(int status);
 /* Extent of H along the shift axes.  Replaces Backend._n_transforms, tnmf/backends/_Backend.py:60-73. */
 int tnmf_transform_shape(const tnmf_problem *p, int32_t *t_shape /* [ndim] */);
 
-/* Bytes of scratch the calls below need for this problem (split-K partials of the W gradient, per-block
- * energy partials).  Always a multiple of 256. */
+/* Bytes of scratch the calls below need for this problem (pre-arranged atom slices, split-K partials of the
+ * W gradient, per-block energy partials).  Always a multiple of 256; the workspace must be 256-byte aligned.
+ * The calls of one problem may share one workspace as long as they are ordered on one stream. */
 size_t tnmf_workspace_bytes(const tnmf_problem *p);
 
-/* 1 if the register-tiled FP32 kernels serve this problem, 0 if the generic kernels do. */
+/* 1 if shared-memory staged FP32 kernels (TMA or cp.async) serve this problem, 0 if the generic kernels do. */
 int tnmf_uses_tiled_path(const tnmf_problem *p);
+
+/* The TNMF_PATH_* family that serves operation `op` (TNMF_OP_*) of this problem, or -1 if the problem is malformed /
+ * the forced `path` cannot serve it. */
+int tnmf_kernel_family(const tnmf_problem *p, int op);
 
 /* R[n,c,d] = sum_m sum_a W[m,c,a] * Hpad[n,m,d+p-a].
  * Replaces Backend.reconstruct, tnmf/backends/_Backend.py:120-122 (NumPy.py:122-132, PyTorch.py:26-43). */
-int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *R, void *stream);
+int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *R, void *workspace,
+                     size_t workspace_bytes, void *stream);
 
 /* *energy (a double in device memory) = 0.5 * sum (V - reconstruct(W,H))^2, reduced on the device; if R is
  * non-null the reconstruction is stored as well.
@@ -100,7 +113,7 @@ int tnmf_reconstruct_energy(const tnmf_problem *p, const void *V, const void *W,
  * R must hold reconstruct(W,H).  neg and pos are contiguous [n,m,*T].
  * Replaces Backend.reconstruction_gradient_H, tnmf/backends/_Backend.py:110-118 (NumPy.py:93-120). */
 int tnmf_gradient_h(const tnmf_problem *p, const void *V, const void *R, const void *W,
-                    void *neg, void *pos, void *stream);
+                    void *neg, void *pos, void *workspace, size_t workspace_bytes, void *stream);
 
 /* Fused H update: the two correlations above plus, in the epilogue and in the reference's order of
  * roundings,   pos += lambda * (G - H);  pos += lambda_cross * (Gsum - G);  pos += reg;  H = (H*neg)/pos
@@ -111,7 +124,7 @@ int tnmf_gradient_h(const tnmf_problem *p, const void *V, const void *R, const v
  * tnmf/TransformInvariantNMF.py:217-235,246-271. */
 int tnmf_update_h(const tnmf_problem *p, const void *V, const void *R, const void *W, void *H,
                   double reg, const void *G, double lambda, const void *Gsum, double lambda_cross,
-                  void *stream);
+                  void *workspace, size_t workspace_bytes, void *stream);
 
 /* neg[m,c,a] = sum_n sum_d Hpad[n,m,d+p-a] * V[n,c,d],  pos likewise from R (R must hold reconstruct(W,H)).
  * Split-K over samples and positions into per-block partials in `workspace`, then a fixed-order

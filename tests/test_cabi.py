@@ -45,7 +45,7 @@ def test_transform_shape_follows_reference(lib, mode, expected):
 
 def test_argument_validation(lib):
     p = _lib.make_problem(3, 2, 4, (20,), (5,), _lib.TNMF_F32)
-    assert lib.tnmf_reconstruct(ctypes.byref(p), None, None, None, None) == _lib.TNMF_EINVAL
+    assert lib.tnmf_reconstruct(ctypes.byref(p), None, None, None, None, 0, None) == _lib.TNMF_EINVAL
     assert lib.tnmf_workspace_bytes(ctypes.byref(p)) % 256 == 0 and lib.tnmf_workspace_bytes(ctypes.byref(p)) > 0
     p.mode = 7
     assert lib.tnmf_workspace_bytes(ctypes.byref(p)) == 0
@@ -75,6 +75,24 @@ def test_tiled_path_selection(lib):
     assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_2d)) == 1
     assert lib.tnmf_uses_tiled_path(ctypes.byref(f64_2d)) == 0
     assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_3d)) == 0
+    # operation by operation: TMA where the strides allow it (H rows of 266 floats are not 16-byte multiples)
+    fam = lambda p, op: lib.tnmf_kernel_family(ctypes.byref(p), op)
+    assert fam(f32_2d, _lib.OP_GRADIENT_H) == _lib.PATHS['tma']
+    assert fam(f32_2d, _lib.OP_RECONSTRUCT) == _lib.PATHS['tiled']
+    padded = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, h_pitch=268)
+    assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
+    circ = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, 'circular')
+    assert [fam(circ, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
+    one_d = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32)
+    assert [fam(one_d, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
+    assert fam(f64_2d, _lib.OP_GRADIENT_W) == _lib.PATHS['generic']
+    padded.path = _lib.PATHS['tma']
+    assert fam(padded, 0) == _lib.PATHS['tma']
+    one_d.path = _lib.PATHS['tma']
+    assert fam(one_d, 0) == -1
+    assert lib.tnmf_workspace_bytes(ctypes.byref(padded)) % 256 == 0
+    bad_pitch = _lib.make_problem(2, 1, 2, (16, 16), (3, 3), _lib.TNMF_F32, h_pitch=10)    # narrower than a row
+    assert fam(bad_pitch, 0) == -1
     f32_2d.path = _lib.PATHS['generic']
     assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_2d)) == 0
 

@@ -279,6 +279,65 @@ def test_tiled_vs_oracle(case, mode):
     assert np.allclose(Wd.sum(dim=tuple(range(2, Wd.dim()))).cpu().numpy(), 1.0, atol=1e-5)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# persistent TMA kernels against the oracle: 2-D, 'valid' / 'full', sample rows a multiple of 16 bytes
+# ---------------------------------------------------------------------------------------------------------
+TMA_CASES = [
+    # N, C, M, D, A
+    (2, 3, 4, (40, 72), (11, 11)),      # cfg2-like atoms, ragged tile edges, padded H rows (82 -> 84)
+    (3, 1, 5, (33, 64), (15, 15)),      # cfg3-like atoms
+    (2, 1, 3, (20, 88), (7, 20)),       # atom wider than the ax-chunk (multi-chunk path)
+    (1, 5, 2, (9, 12), (3, 2)),         # more channels than a channel block, even atom width
+    (4, 1, 1, (17, 16), (1, 1)),        # single atom of one pixel
+    (2, 2, 3, (6, 8), (6, 8)),          # atom as large as the sample ('full': a single activation)
+    (1, 1, 2, (70, 300), (5, 64)),      # wide atom, wide sample
+    (3, 3, 16, (64, 64), (11, 11)),     # several atom blocks, several work units per CTA
+    (5, 2, 9, (100, 36), (4, 9)),       # unbalanced atom blocks (9 = 3 x 3), tall samples
+]
+
+
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+@pytest.mark.parametrize('case', range(len(TMA_CASES)))
+def test_tma_vs_oracle(case, mode):
+    N, C, M, D, A = TMA_CASES[case]
+    rng = np.random.default_rng(200 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'auto')
+    tol = 2e-5
+    R = orc.reconstruct(W64, H64, mode)
+    _close(be.reconstruct(Wd, Hd), R, tol)
+    # TMA boxes must start on a multiple of 4 elements: always possible for the H update (shifted tile origin), for
+    # the other two only when off - (A_x - 1) is a multiple of 4 ('valid': always); else the cp.async kernels serve
+    h_side = 'tma' if (mode == 'valid' or (A[-1] - 1) % 4 == 0) else 'tiled'
+    assert be.kernel_families() == {'reconstruct': h_side, 'update_h': 'tma', 'gradient_w': h_side}
+    neg, pos = be.reconstruction_gradient_H(V, Wd, Hd)
+    rn, rp = orc.reconstruction_gradient_H(V64, W64, H64, mode)
+    _close(neg, rn, tol)
+    _close(pos, rp, tol)
+    neg, pos = be.reconstruction_gradient_W(V, Wd, Hd)
+    rn, rp = orc.reconstruction_gradient_W(V64, W64, H64, mode)
+    _close(neg, rn, tol)
+    _close(pos, rp, tol)
+    assert np.isclose(be.reconstruction_energy(V, Wd, Hd), orc.reconstruction_energy(V64, W64, H64, mode), rtol=2e-5)
+    # partial reconstruction: a strided single-atom view of H (tnmf/backends/_Backend.py:124-125)
+    _close(be.partial_reconstruct(Wd, Hd, M - 1), orc.reconstruct(W64[M - 1:], H64[:, M - 1:], mode), tol)
+    # fused update with every epilogue term against the oracle's update, on a sample slice and on the rest
+    nmf = orc.OracleNMF(M, A, reconstruction_mode=mode)
+    nmf.V, nmf.W, nmf.H = V64, W64.copy(), H64.copy()
+    for s in (slice(0, 1), slice(1, N)):
+        nmf.update_H(s, sparsity=0.1, inhibition=0.2, cross_inhibition=0.3 if M > 1 else 0.0)
+        be.update_H(V, Wd, Hd, s, 0.1, 0.2, 0.3 if M > 1 else 0.0, nmf.inhibition_kernels)
+    _close(Hd, nmf.H, 5e-5)
+    nmf.update_W()
+    grad = torch.empty((2, *Wd.shape), dtype=Wd.dtype, device=Wd.device)
+    be.apply_W_update(Wd, be.gradient_W(V, Wd, Hd, slice(None), grad))
+    _close(Wd, nmf.W, 5e-5)
+    assert np.allclose(Wd.sum(dim=tuple(range(2, Wd.dim()))).cpu().numpy(), 1.0, atol=1e-5)
+
+
 def test_empty_and_single_sample_batches():
     """Ragged minibatches: an empty slice contributes a zero W gradient, a short last batch is served."""
     rng = np.random.default_rng(7)

@@ -14,11 +14,11 @@ from typing import Optional, Sequence
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libtnmf_b200.so')
-SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu')
+SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu', 'tma_kernels.cu')
 # compiled once per atom-width chunk (-DTNMF_AXC=...): the register-tiled kernels
-CHUNKED_SOURCES = ('tiled_recon.cu', 'tiled_hupd.cu', 'tiled_gradw.cu')
+CHUNKED_SOURCES = ('tiled_recon.cu', 'tiled_hupd.cu', 'tiled_gradw.cu', 'tma_recon.cu', 'tma_hupd.cu', 'tma_gradw.cu')
 CHUNKS = (4, 8, 12, 16)
-HEADERS = ('common.cuh', 'tiled_common.cuh', os.path.join('..', '..', 'include', 'tnmf_b200.h'))
+HEADERS = ('common.cuh', 'tiled_common.cuh', 'tma_common.cuh', os.path.join('..', '..', 'include', 'tnmf_b200.h'))
 
 # NB: no --use_fast_math: divisions must round like the reference's IEEE arithmetic.
 NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -26,9 +26,10 @@ NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 
 TNMF_F32, TNMF_F64 = 0, 1
 MODES = {'valid': 0, 'full': 1, 'circular': 2}
-PATHS = {'auto': 0, 'generic': 1, 'tiled': 2}
+PATHS = {'auto': 0, 'generic': 1, 'tiled': 2, 'tma': 3}
+OP_RECONSTRUCT, OP_GRADIENT_H, OP_GRADIENT_W = 0, 1, 2
 TNMF_OK, TNMF_EINVAL, TNMF_EUNSUPPORTED, TNMF_EWORKSPACE, TNMF_ECUDA = 0, 1, 2, 3, 1000
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class Problem(ctypes.Structure):
@@ -36,7 +37,7 @@ class Problem(ctypes.Structure):
     _fields_ = [
         ('ndim', ctypes.c_int32), ('dtype', ctypes.c_int32), ('mode', ctypes.c_int32), ('path', ctypes.c_int32),
         ('n_samples', ctypes.c_int32), ('n_channels', ctypes.c_int32), ('n_atoms', ctypes.c_int32),
-        ('reserved', ctypes.c_int32),
+        ('h_pitch', ctypes.c_int32),
         ('sample_shape', ctypes.c_int32 * 3), ('atom_shape', ctypes.c_int32 * 3),
         ('h_stride_n', ctypes.c_int64), ('h_stride_m', ctypes.c_int64),
     ]
@@ -52,10 +53,11 @@ SIGNATURES = {
     'tnmf_transform_shape': (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int32)]),
     'tnmf_workspace_bytes': (_sz, [_P]),
     'tnmf_uses_tiled_path': (ctypes.c_int, [_P]),
-    'tnmf_reconstruct': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp]),
+    'tnmf_kernel_family': (ctypes.c_int, [_P, ctypes.c_int]),
+    'tnmf_reconstruct': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _sz, _vp]),
     'tnmf_reconstruct_energy': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    'tnmf_gradient_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp]),
-    'tnmf_update_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _dbl, _vp, _dbl, _vp, _dbl, _vp]),
+    'tnmf_gradient_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    'tnmf_update_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _dbl, _vp, _dbl, _vp, _dbl, _vp, _sz, _vp]),
     'tnmf_gradient_w': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'tnmf_update_w': (ctypes.c_int, [_P, _vp, _vp, _vp, _dbl, _vp]),
     'tnmf_normalize': (ctypes.c_int, [_i32, _vp, _i64, _i64, _i64, _vp]),
@@ -151,7 +153,7 @@ def check(status: int, what: str = '') -> None:
 
 def make_problem(n_samples: int, n_channels: int, n_atoms: int, sample_shape: Sequence[int],
                  atom_shape: Sequence[int], dtype_code: int, mode: str = 'valid', path: str = 'auto',
-                 h_stride_n: int = 0, h_stride_m: int = 0) -> Problem:
+                 h_stride_n: int = 0, h_stride_m: int = 0, h_pitch: int = 0) -> Problem:
     if mode not in MODES:
         raise ValueError(f'Unsupported reconstruction mode "{mode}". Please choose "valid", "full" or "circular".')
     if len(sample_shape) != len(atom_shape):
@@ -164,5 +166,5 @@ def make_problem(n_samples: int, n_channels: int, n_atoms: int, sample_shape: Se
     for i, (d, a) in enumerate(zip(sample_shape, atom_shape)):
         p.sample_shape[i] = int(d)
         p.atom_shape[i] = int(a)
-    p.h_stride_n, p.h_stride_m = int(h_stride_n), int(h_stride_m)
+    p.h_stride_n, p.h_stride_m, p.h_pitch = int(h_stride_n), int(h_stride_m), int(h_pitch)
     return p

@@ -74,6 +74,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self._energy_buf = None
         self._problems = {}
         self._taps = {}
+        self._last_h_problem = None
         self.launches = 0       # number of kernels of this library launched so far (bench.py reports it)
         self.kernel_events = None   # set to {} to record a (start, end) CUDA-event pair around every hot-path call
 
@@ -115,12 +116,12 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self._V_src, self._V_dev = V, dev
         return dev
 
-    def _problem(self, n: int, n_atoms: int, hsn: int = 0, hsm: int = 0) -> _lib.Problem:
-        key = (n, n_atoms, hsn, hsm)
+    def _problem(self, n: int, n_atoms: int, hsn: int = 0, hsm: int = 0, pitch: int = 0) -> _lib.Problem:
+        key = (n, n_atoms, hsn, hsm, pitch)
         p = self._problems.get(key)
         if p is None:
             p = _lib.make_problem(n, self.n_channels, n_atoms, self._sample_shape, self.atom_shape,
-                                  _DTYPE_CODE[self._dtype], self._reconstruction_mode, self._path, hsn, hsm)
+                                  _DTYPE_CODE[self._dtype], self._reconstruction_mode, self._path, hsn, hsm, pitch)
             self._problems[key] = p
         return p
 
@@ -128,20 +129,49 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         """Problem descriptor for an activation tensor that may be a view (leading-axis slice, single atom)."""
         k = len(self.atom_shape)
         tail = H.shape[2:]
-        expect = 1
-        ok = True
-        for size, stride in zip(reversed(tail), reversed(H.stride()[2:])):
-            if size != 1 and stride != expect:
-                ok = False
-            expect *= size
+        assert len(tail) == k
+        # the last axis must be dense; the second-to-last may carry a padded pitch (see `initialize`); any
+        # axis before that must follow densely from the pitch
+        strides = H.stride()[2:]
+        pitch = int(tail[-1])
+        ok = tail[-1] == 1 or strides[-1] == 1
+        if k >= 2:
+            if tail[-2] != 1:
+                pitch = int(strides[-2])
+                ok = ok and pitch >= tail[-1]
+            expect = pitch * tail[-2]
+            for size, stride in zip(reversed(tail[:-2]), reversed(strides[:-2])):
+                if size != 1 and stride != expect:
+                    ok = False
+                expect *= size
         if not ok:
             H = H.contiguous()
-        assert len(tail) == k
+            pitch = int(tail[-1])
         hsn, hsm = max(int(H.stride(0)), 1), max(int(H.stride(1)), 1)   # strides of size-1 axes are never used
-        return self._problem(H.shape[0], H.shape[1], hsn, hsm), H
+        p = self._problem(H.shape[0], H.shape[1], hsn, hsm, 0 if pitch == tail[-1] else pitch)
+        self._last_h_problem = p
+        return p, H
+
+    def _alloc_H(self, shape, random: bool) -> torch.Tensor:
+        """Activation tensor of the reference's shape [n, M, *T].  For float32 problems with two shift axes the
+        rows are padded to a multiple of 4 elements (16 bytes) - the TMA kernels cut their boxes out of H and need
+        that stride alignment - and the returned tensor is the [..., :T_x] view of the padded buffer."""
+        pad = (-shape[-1]) % 4
+        if self._dtype != torch.float32 or len(self.atom_shape) != 2 or pad == 0 or self._path == 'generic':
+            if random:
+                return 1 - torch.rand(shape, dtype=self._dtype, device=self.device)
+            return torch.empty(shape, dtype=self._dtype, device=self.device)
+        padded = (*shape[:-1], shape[-1] + pad)
+        buf = torch.rand(padded, dtype=self._dtype, device=self.device) if random else \
+            torch.empty(padded, dtype=self._dtype, device=self.device)
+        if random:
+            buf.neg_().add_(1)
+        return buf[..., :shape[-1]]
 
     def _workspace(self, p: _lib.Problem) -> Tuple[torch.Tensor, int]:
-        need = int(self._lib.tnmf_workspace_bytes(ctypes.byref(p)))
+        need = getattr(p, 'ws_need', None)
+        if need is None:
+            need = p.ws_need = int(self._lib.tnmf_workspace_bytes(ctypes.byref(p)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
         return self._ws, self._ws.numel()
@@ -152,6 +182,15 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         if self._R_buf is None or self._R_buf.numel() < numel or self._R_buf.dtype != self._dtype:
             self._R_buf = torch.empty(max(numel, 1), dtype=self._dtype, device=self.device)
         return self._R_buf[:numel].view(shape)
+
+    def kernel_families(self, n: Optional[int] = None) -> dict:
+        """Which kernel family (generic / tiled / tma) serves each hot-path operation of the current problem."""
+        names = {v: k for k, v in _lib.PATHS.items()}
+        p, _ = self._h_problem(self._alloc_H((1 if n is None else n, self.n_atoms, *self._transform_shape), False)) \
+            if n is not None else (self._last_h_problem, None)
+        return {op: names.get(int(self._lib.tnmf_kernel_family(ctypes.byref(p), code)), 'none')
+                for op, code in (('reconstruct', _lib.OP_RECONSTRUCT), ('update_h', _lib.OP_GRADIENT_H),
+                                 ('gradient_w', _lib.OP_GRADIENT_W))}
 
     def uses_tiled_kernels(self, n: Optional[int] = None) -> bool:
         p = self._problem(self.n_samples if n is None else n, self.n_atoms)
@@ -205,14 +244,15 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             # identical stream of random numbers as the reference: H first, then W, float64 draws cast to V.dtype
             np_dtype = np.float32 if self._dtype == torch.float32 else np.float64
             h_host = np.asarray(1 - np.random.rand(n_total, self.n_atoms, *self._transform_shape), dtype=np_dtype)
-            H = self._to_device(h_host[lo:hi])
+            H = self._alloc_H(h_shape, random=False)
+            H.copy_(torch.from_numpy(h_host[lo:hi]))
             del h_host
             if W is None:
                 w_host = np.asarray(1 - np.random.rand(*w_shape), dtype=np_dtype)
                 W = self._to_device(w_host)
                 self.normalize(W, axes_W_normalization)
         else:
-            H = 1 - torch.rand(h_shape, dtype=self._dtype, device=self.device)
+            H = self._alloc_H(h_shape, random=True)
             if W is None:
                 W = 1 - torch.rand(w_shape, dtype=self._dtype, device=self.device)
                 self.normalize(W, axes_W_normalization)
@@ -225,7 +265,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
     @staticmethod
     def to_ndarray(arr) -> np.ndarray:
         if isinstance(arr, torch.Tensor):
-            return arr.detach().cpu().numpy()
+            return np.ascontiguousarray(arr.detach().cpu().numpy())
         return np.asarray(arr)
 
     # -----------------------------------------------------------------------------------------------
@@ -284,11 +324,20 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         W = W if W.is_contiguous() else W.contiguous()
         R = out if out is not None else torch.empty((H.shape[0], self.n_channels, *self._sample_shape),
                                                     dtype=self._dtype, device=self.device)
+        ws, ws_bytes = self._workspace(p)
         with self._timed('reconstruct'):
             _lib.check(self._lib.tnmf_reconstruct(ctypes.byref(p), W.data_ptr(), H.data_ptr(), R.data_ptr(),
-                                                  _stream_ptr(self.device)), 'reconstruct')
-        self.launches += 1
+                                                  ws.data_ptr(), ws_bytes, _stream_ptr(self.device)), 'reconstruct')
+        self.launches += self._n_launches(p, _lib.OP_RECONSTRUCT)
         return R
+
+    def _n_launches(self, p: _lib.Problem, op: int) -> int:
+        """Kernels one call of operation `op` launches (the TMA family pre-arranges the atoms in a tiny extra
+        kernel; the W gradient always has its finishing reduction)."""
+        fam = int(self._lib.tnmf_kernel_family(ctypes.byref(p), op))
+        if op == _lib.OP_GRADIENT_W:
+            return 2
+        return 2 if fam == _lib.PATHS['tma'] else 1
 
     def reconstruction_gradient_H(self, V, W, H, s: slice = sliceNone):
         """(neg, pos) with the shape of H[s]   (tnmf/backends/_Backend.py:110-118)."""
@@ -298,9 +347,11 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         p = self._problem(Hs.shape[0], self.n_atoms)
         neg = torch.empty(Hs.shape, dtype=self._dtype, device=self.device)
         pos = torch.empty_like(neg)
+        ws, ws_bytes = self._workspace(p)
         _lib.check(self._lib.tnmf_gradient_h(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), W.data_ptr(),
-                                             neg.data_ptr(), pos.data_ptr(), _stream_ptr(self.device)), 'gradient_h')
-        self.launches += 1
+                                             neg.data_ptr(), pos.data_ptr(), ws.data_ptr(), ws_bytes,
+                                             _stream_ptr(self.device)), 'gradient_h')
+        self.launches += self._n_launches(p, _lib.OP_GRADIENT_H)
         return neg, pos
 
     def reconstruction_gradient_W(self, V, W, H, s: slice = sliceNone):
@@ -326,7 +377,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         _lib.check(self._lib.tnmf_reconstruct_energy(ctypes.byref(p), Vs.data_ptr(), W.data_ptr(), Hs.data_ptr(), None,
                                                      e.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(self.device)),
                    'reconstruct_energy')
-        self.launches += 2
+        self.launches += 1 + self._n_launches(p, _lib.OP_RECONSTRUCT)
         return e
 
     def _inhibition_taps(self, kernels: Sequence[np.ndarray]):
@@ -345,18 +396,17 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         Hs = H[s]
         if Hs.shape[0] == 0:
             return
-        assert Hs.is_contiguous()
         Vs = self._device_V(V)[s]
         n = Hs.shape[0]
         R = self.reconstruct(W, Hs, out=self._R_for(n))
-        p = self._problem(n, self.n_atoms)
+        p, Hs = self._h_problem(Hs)
         G_ptr, Gsum_ptr = None, None
         lam, lam_cross = 0.0, 0.0
         st = _stream_ptr(self.device)
         if inhibition > 0 or cross_inhibition > 0:
             taps = self._inhibition_taps(inhibition_kernels)
             code = _DTYPE_CODE[self._dtype]
-            G = Hs
+            G = Hs.contiguous()      # the separable convolution reads dense [outer, len, inner] views
             k = len(self.atom_shape)
             for i, tp in enumerate(taps):
                 axis = Hs.dim() - k + i
@@ -378,11 +428,12 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
                 Gsum_ptr = Gsum.data_ptr()
                 lam_cross = float(cross_inhibition) / (self.n_atoms - 1)
         reg = eps + sparsity if sparsity > 0 else eps
+        ws, ws_bytes = self._workspace(p)
         with self._timed('update_h'):
             _lib.check(self._lib.tnmf_update_h(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), W.data_ptr(),
-                                               Hs.data_ptr(), float(reg), G_ptr, lam, Gsum_ptr, lam_cross, st),
-                       'update_h')
-        self.launches += 1
+                                               Hs.data_ptr(), float(reg), G_ptr, lam, Gsum_ptr, lam_cross,
+                                               ws.data_ptr(), ws_bytes, st), 'update_h')
+        self.launches += self._n_launches(p, _lib.OP_GRADIENT_H)
 
     def gradient_W(self, V, W, H, s: slice, out: torch.Tensor) -> torch.Tensor:
         """out[0] = neg, out[1] = pos of the W gradient on samples s (split-K + deterministic final reduction)."""

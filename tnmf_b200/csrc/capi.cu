@@ -6,6 +6,8 @@
 
 using namespace tnmf;
 
+static bool aligned16(const void *p) { return (reinterpret_cast<unsigned long long>(p) & 15ull) == 0; }
+
 namespace {
 
 int make_geo(const tnmf_problem *p, Geo &g) {
@@ -29,21 +31,31 @@ int make_geo(const tnmf_problem *p, Geo &g) {
         g.D[lead + i] = d; g.A[lead + i] = a; g.T[lead + i] = t;
         g.off[lead + i] = p->mode == TNMF_VALID ? a - 1 : 0;
     }
-    const long long tvol = vol3(g.T);
+    if (p->h_pitch != 0 && p->h_pitch < g.T[2]) return TNMF_EINVAL;
+    g.hsy = p->h_pitch ? p->h_pitch : g.T[2];
+    const long long tvol = (long long)g.T[0] * g.T[1] * g.hsy;
     g.hsm = p->h_stride_m ? p->h_stride_m : tvol;
     g.hsn = p->h_stride_n ? p->h_stride_n : tvol * g.M;
     return TNMF_OK;
 }
 
-bool use_tiled(const tnmf_problem *p, const Geo &g, int *err) {
+// Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;
+// a forced family that cannot serve the problem is an error.
+int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
     *err = TNMF_OK;
-    const bool ok = tiled_supported(g, p->dtype);
-    if (p->path == TNMF_PATH_GENERIC) return false;
-    if (p->path == TNMF_PATH_TILED) {
-        if (!ok) *err = TNMF_EUNSUPPORTED;
-        return ok;
+    if (p->path == TNMF_PATH_GENERIC) return TNMF_PATH_GENERIC;
+    bool tma_ok = false;
+    if (p->path == TNMF_PATH_AUTO || p->path == TNMF_PATH_TMA) {
+        if (op == TNMF_OP_RECONSTRUCT) tma_ok = tma_recon_supported(g, p->dtype);
+        else if (op == TNMF_OP_GRADIENT_H) tma_ok = tma_hupd_supported(g, p->dtype);
+        else tma_ok = tma_gradw_supported(g, p->dtype);
     }
-    return ok;
+    if (tma_ok) return TNMF_PATH_TMA;
+    if (p->path == TNMF_PATH_TMA) { *err = TNMF_EUNSUPPORTED; return -1; }
+    const bool tiled_ok = tiled_supported(g, p->dtype);
+    if (tiled_ok) return TNMF_PATH_TILED;
+    if (p->path == TNMF_PATH_TILED) { *err = TNMF_EUNSUPPORTED; return -1; }
+    return TNMF_PATH_GENERIC;
 }
 
 size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -92,6 +104,8 @@ size_t tnmf_workspace_bytes(const tnmf_problem *p) {
         const size_t t = align256(tiled_workspace_bytes(g));
         if (t > bytes) bytes = t;
     }
+    const size_t t = tma_workspace_bytes(g, p->dtype);
+    if (t > bytes) bytes = t;
     return bytes;
 }
 
@@ -99,18 +113,36 @@ int tnmf_uses_tiled_path(const tnmf_problem *p) {
     Geo g;
     if (make_geo(p, g)) return 0;
     int err;
-    return use_tiled(p, g, &err) ? 1 : 0;
+    const int f = choose_family(p, g, TNMF_OP_GRADIENT_H, &err);
+    return (f == TNMF_PATH_TILED || f == TNMF_PATH_TMA) ? 1 : 0;
 }
 
-int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *R, void *stream) {
+int tnmf_kernel_family(const tnmf_problem *p, int op) {
+    Geo g;
+    if (make_geo(p, g)) return -1;
+    if (op < TNMF_OP_RECONSTRUCT || op > TNMF_OP_GRADIENT_W) return -1;
+    int err;
+    return choose_family(p, g, op, &err);
+}
+
+int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *R, void *workspace,
+                     size_t workspace_bytes, void *stream) {
     Geo g;
     int s = make_geo(p, g);
     if (s) return s;
     if (!W || !H || !R) return TNMF_EINVAL;
     if (g.N == 0) return TNMF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool tiled = use_tiled(p, g, &s);
+    int family = choose_family(p, g, TNMF_OP_RECONSTRUCT, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TMA && (!aligned16(H) || !workspace)) {
+        if (p->path == TNMF_PATH_TMA) return workspace ? TNMF_EUNSUPPORTED : TNMF_EWORKSPACE;
+        family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
+    }
+    if (family == TNMF_PATH_TMA)
+        return tma_reconstruct(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, workspace,
+                               workspace_bytes, st);
+    const bool tiled = family == TNMF_PATH_TILED;
     if (tiled)
         return tiled_reconstruct(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
     if (p->dtype == TNMF_F32)
@@ -134,9 +166,18 @@ int tnmf_reconstruct_energy(const tnmf_problem *p, const void *V, const void *W,
         cudaError_t e = cudaMemsetAsync(energy, 0, sizeof(double), st);
         return status_from_cuda(e);
     }
-    const bool tiled = use_tiled(p, g, &s);
+    int family = choose_family(p, g, TNMF_OP_RECONSTRUCT, &s);
     if (s) return s;
-    if (tiled)
+    if (family == TNMF_PATH_TMA && !aligned16(H)) {
+        if (p->path == TNMF_PATH_TMA) return TNMF_EUNSUPPORTED;
+        family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
+    }
+    const bool tiled = family == TNMF_PATH_TILED;
+    if (family == TNMF_PATH_TMA) {
+        partials = tma_energy_partials(g, workspace);
+        s = tma_reconstruct(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials,
+                            workspace, workspace_bytes, st);
+    } else if (tiled)
         s = tiled_reconstruct(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials,
                               &n_partials, st);
     else if (p->dtype == TNMF_F32)
@@ -151,15 +192,24 @@ int tnmf_reconstruct_energy(const tnmf_problem *p, const void *V, const void *W,
 
 static int gradient_h_dispatch(const tnmf_problem *p, const void *V, const void *R, const void *W, void *neg,
                                void *pos, void *H, double reg, const void *G, double lambda, const void *Gsum,
-                               double lambda_cross, void *stream) {
+                               double lambda_cross, void *workspace, size_t workspace_bytes, void *stream) {
     Geo g;
     int s = make_geo(p, g);
     if (s) return s;
     if (!V || !R || !W) return TNMF_EINVAL;
     if (g.N == 0) return TNMF_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool tiled = use_tiled(p, g, &s);
+    int family = choose_family(p, g, TNMF_OP_GRADIENT_H, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TMA && (!aligned16(V) || !aligned16(R) || !workspace)) {
+        if (p->path == TNMF_PATH_TMA) return workspace ? TNMF_EUNSUPPORTED : TNMF_EWORKSPACE;
+        family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
+    }
+    if (family == TNMF_PATH_TMA)
+        return tma_gradient_h(g, (const float *)V, (const float *)R, (const float *)W, (float *)neg, (float *)pos,
+                              (float *)H, reg, (const float *)G, lambda, (const float *)Gsum, lambda_cross, workspace,
+                              workspace_bytes, st);
+    const bool tiled = family == TNMF_PATH_TILED;
     if (tiled)
         return tiled_gradient_h(g, (const float *)V, (const float *)R, (const float *)W, (float *)neg, (float *)pos,
                                 (float *)H, reg, (const float *)G, lambda, (const float *)Gsum, lambda_cross, st);
@@ -173,19 +223,22 @@ static int gradient_h_dispatch(const tnmf_problem *p, const void *V, const void 
 }
 
 int tnmf_gradient_h(const tnmf_problem *p, const void *V, const void *R, const void *W, void *neg, void *pos,
-                    void *stream) {
+                    void *workspace, size_t workspace_bytes, void *stream) {
     if (!neg || !pos) return TNMF_EINVAL;
-    return gradient_h_dispatch(p, V, R, W, neg, pos, nullptr, 0.0, nullptr, 0.0, nullptr, 0.0, stream);
+    return gradient_h_dispatch(p, V, R, W, neg, pos, nullptr, 0.0, nullptr, 0.0, nullptr, 0.0, workspace,
+                               workspace_bytes, stream);
 }
 
 int tnmf_update_h(const tnmf_problem *p, const void *V, const void *R, const void *W, void *H, double reg,
-                  const void *G, double lambda, const void *Gsum, double lambda_cross, void *stream) {
+                  const void *G, double lambda, const void *Gsum, double lambda_cross, void *workspace,
+                  size_t workspace_bytes, void *stream) {
     if (!H) return TNMF_EINVAL;
     if (lambda_cross != 0.0 && !Gsum) return TNMF_EINVAL;
     if (lambda_cross == 0.0) Gsum = nullptr;
     if (lambda == 0.0 && !Gsum) G = nullptr;
     if ((lambda != 0.0 || Gsum) && !G) return TNMF_EINVAL;
-    return gradient_h_dispatch(p, V, R, W, nullptr, nullptr, H, reg, G, lambda, Gsum, lambda_cross, stream);
+    return gradient_h_dispatch(p, V, R, W, nullptr, nullptr, H, reg, G, lambda, Gsum, lambda_cross, workspace,
+                               workspace_bytes, stream);
 }
 
 int tnmf_gradient_w(const tnmf_problem *p, const void *V, const void *R, const void *H, void *neg, void *pos,
@@ -202,8 +255,18 @@ int tnmf_gradient_w(const tnmf_problem *p, const void *V, const void *R, const v
         if (e == cudaSuccess) e = cudaMemsetAsync(pos, 0, count * esz, st);
         return status_from_cuda(e);
     }
-    const bool tiled = use_tiled(p, g, &s);
+    int family = choose_family(p, g, TNMF_OP_GRADIENT_W, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TMA && (!aligned16(V) || !aligned16(R) || !aligned16(H))) {
+        if (p->path == TNMF_PATH_TMA) return TNMF_EUNSUPPORTED;
+        family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
+    }
+    if (family == TNMF_PATH_TMA) {
+        if (!workspace || workspace_bytes < tnmf_workspace_bytes(p)) return TNMF_EWORKSPACE;
+        return tma_gradient_w(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,
+                              workspace, workspace_bytes, st);
+    }
+    const bool tiled = family == TNMF_PATH_TILED;
     if (tiled) {
         if (!workspace || workspace_bytes < tnmf_workspace_bytes(p)) return TNMF_EWORKSPACE;
         return tiled_gradient_w(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,

@@ -27,6 +27,7 @@ struct Geo {
     int wrap;      // 1 for 'circular'
     int ndim;
     long long hsn, hsm;   // element strides of H's leading axes
+    long long hsy;        // element stride between rows of H (>= T[2]; the last axis is always dense)
 };
 
 __host__ __device__ inline long long vol3(const int *s) { return (long long)s[0] * s[1] * s[2]; }
@@ -69,6 +70,20 @@ int tiled_gradient_h(const Geo &g, const float *V, const float *R, const float *
                      double lambda_cross, cudaStream_t st);
 int tiled_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos,
                      void *workspace, size_t workspace_bytes, cudaStream_t st);
+
+// ---- implemented in tma_kernels.cu ------------------------------------------------------------------------
+bool tma_recon_supported(const Geo &g, int dtype);
+bool tma_hupd_supported(const Geo &g, int dtype);
+bool tma_gradw_supported(const Geo &g, int dtype);
+size_t tma_workspace_bytes(const Geo &g, int dtype);
+double *tma_energy_partials(const Geo &g, void *workspace);
+int tma_reconstruct(const Geo &g, const float *W, const float *H, float *R, const float *V, double *energy_partials,
+                    int *n_partials, void *workspace, size_t workspace_bytes, cudaStream_t st);
+int tma_gradient_h(const Geo &g, const float *V, const float *R, const float *W, float *neg, float *pos, float *H,
+                   double reg, const float *G, double lambda, const float *Gsum, double lambda_cross, void *workspace,
+                   size_t workspace_bytes, cudaStream_t st);
+int tma_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos,
+                   void *workspace, size_t workspace_bytes, cudaStream_t st);
 
 // ---- implemented in elementwise.cu ----------------------------------------------------------------------
 int finish_energy(const double *partials, int n, double *energy, cudaStream_t st);

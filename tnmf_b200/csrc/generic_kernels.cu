@@ -51,7 +51,7 @@ generic_reconstruct_kernel(Geo g, const T *__restrict__ W, const T *__restrict__
                 for (int ay = 0; ay < g.A[1]; ++ay) {
                     int ty = y + g.off[1] - ay;
                     if (!fold_index(ty, g.T[1], g.wrap)) continue;
-                    const T *hrow = h + ((long long)tz * g.T[1] + ty) * g.T[2];
+                    const T *hrow = h + ((long long)tz * g.T[1] + ty) * g.hsy;
                     const T *wrow = w + ((long long)az * g.A[1] + ay) * g.A[2];
                     for (int ax = 0; ax < g.A[2]; ++ax) {
                         int tx = x + g.off[2] - ax;
@@ -114,7 +114,7 @@ generic_gradient_h_kernel(Geo g, const T *__restrict__ V, const T *__restrict__ 
         }
         if (H) {
             const long long tin = ((long long)tz * g.T[1] + ty) * g.T[2] + tx;
-            T *hp = H + n * g.hsn + m * g.hsm + tin;
+            T *hp = H + n * g.hsn + m * g.hsm + ((long long)tz * g.T[1] + ty) * g.hsy + tx;
             const T h = *hp;
             if (G) {
                 const T gi = G[idx];
@@ -157,7 +157,7 @@ generic_gradient_w_kernel(Geo g, const T *__restrict__ V, const T *__restrict__ 
         int tz = z + g.off[0] - az, ty = y + g.off[1] - ay, tx = x + g.off[2] - ax;
         if (!fold_index(tz, g.T[0], g.wrap) || !fold_index(ty, g.T[1], g.wrap) || !fold_index(tx, g.T[2], g.wrap))
             continue;
-        const double h = (double)H[n * g.hsn + m * g.hsm + ((long long)tz * g.T[1] + ty) * g.T[2] + tx];
+        const double h = (double)H[n * g.hsn + m * g.hsm + ((long long)tz * g.T[1] + ty) * g.hsy + tx];
         const long long xi = ((long long)n * g.C + c) * dvol + ((long long)z * g.D[1] + y) * g.D[2] + x;
         neg += h * (double)V[xi];
         pos += h * (double)R[xi];

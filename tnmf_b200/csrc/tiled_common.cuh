@@ -23,7 +23,7 @@ struct Geo2 {
     int N, C, M;
     int DY, DX, AY, AX, TY, TX;
     int offy, offx, wrap;
-    long long hsn, hsm;
+    long long hsn, hsm, hsy;
 };
 
 // Atom-width chunking: the atom row is cut into NK chunks of AXC taps (zero-padded to AXP = NK*AXC).
@@ -59,7 +59,7 @@ inline Geo2 make_geo2(const Geo &g) {
     q.N = g.N; q.C = g.C; q.M = g.M;
     q.DY = g.D[1]; q.DX = g.D[2]; q.AY = g.A[1]; q.AX = g.A[2]; q.TY = g.T[1]; q.TX = g.T[2];
     q.offy = g.off[1]; q.offx = g.off[2]; q.wrap = g.wrap;
-    q.hsn = g.hsn; q.hsm = g.hsm;
+    q.hsn = g.hsn; q.hsm = g.hsm; q.hsy = g.hsy;
     return q;
 }
 
@@ -124,13 +124,13 @@ __device__ __forceinline__ void cp_async16n(float *smem_dst, const float *gmem_s
 // (16, 8 or 4 bytes); elements outside the plane are zero-filled through the src-size operand ('wrap': folded).
 // All threads of the block call.
 __device__ __forceinline__ void stage_plane(float *dst, int pitch, const float *__restrict__ plane, int extent_y,
-                                            int extent_x, int gy0, int gx0, int rows, int cols, int wrap, int warp,
-                                            int n_warps, int lane) {
+                                            int extent_x, long long src_pitch, int gy0, int gx0, int rows, int cols,
+                                            int wrap, int warp, int n_warps, int lane) {
     const int units = (cols + 3) >> 2;
     for (int r = warp; r < rows; r += n_warps) {
         int y = gy0 + r;
         const bool row_ok = fold(y, extent_y, wrap);
-        const float *src_row = plane + (long long)(row_ok ? y : 0) * extent_x;
+        const float *src_row = plane + (long long)(row_ok ? y : 0) * src_pitch;
         float *dst_row = dst + r * pitch;
         const int rb = swz_row(r);
         if (wrap) {

@@ -123,7 +123,7 @@ gradw_kernel(const Geo2 g, const GradWPlan p, const float *__restrict__ V, const
         }
         const int by_lo = by_lo_of(ug);
         const int hrows = p.RY + by_hi_of(ug) - by_lo;
-        stage_plane(th, p.pitch_h, H + n * g.hsn + m * g.hsm, g.TY, g.TX, y_base + g0y + by_lo, x_base + g0x, hrows,
+        stage_plane(th, p.pitch_h, H + n * g.hsn + m * g.hsm, g.TY, g.TX, g.hsy, y_base + g0y + by_lo, x_base + g0x, hrows,
                     p.XC + AXP - 1, g.wrap, warp, n_warps, lane);
         cp_async_commit();
     };

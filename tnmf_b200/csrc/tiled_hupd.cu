@@ -55,8 +55,8 @@ hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const f
         float *tr = tv + p.plane_floats;
         float *wt = tr + p.plane_floats;
         const long long plane = ((long long)n * g.C + c) * dvol;
-        stage_plane(tv, p.pitch, V + plane, g.DY, g.DX, gy0, gx0, p.HR, p.WT, g.wrap, warp, n_warps, lane);
-        stage_plane(tr, p.pitch, R + plane, g.DY, g.DX, gy0, gx0, p.HR, p.WT, g.wrap, warp, n_warps, lane);
+        stage_plane(tv, p.pitch, V + plane, g.DY, g.DX, g.DX, gy0, gx0, p.HR, p.WT, g.wrap, warp, n_warps, lane);
+        stage_plane(tr, p.pitch, R + plane, g.DY, g.DX, g.DX, gy0, gx0, p.HR, p.WT, g.wrap, warp, n_warps, lane);
         // zero-padded atom slices: wt[ay][ax/4][i][ax%4] = W[m0+i][c][ay][ax]
         const int qpr = AXP >> 2;
         const int groups = g.AY * qpr * MB;
@@ -133,12 +133,13 @@ hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const f
     const int ty = y0 + ry0, tx = x0 + rx0;
     if (ty >= g.TY || tx >= g.TX) return;
     const long long tvol = (long long)g.TY * g.TX;
-    const long long tin = (long long)ty * g.TX + tx;
+    const long long tin = (long long)ty * g.TX + tx;          // neg / pos / G / Gsum are dense
+    const long long tin_h = (long long)ty * g.hsy + tx;       // H may carry a padded row pitch
     float hv[MB][kCols];
     if (H) {
 #pragma unroll
         for (int i = 0; i < MB; ++i) {                               // all H loads in flight before the first use
-            const float *hp = H + n * g.hsn + (m0 + i < g.M ? m0 + i : m0) * g.hsm + tin;
+            const float *hp = H + n * g.hsn + (m0 + i < g.M ? m0 + i : m0) * g.hsm + tin_h;
 #pragma unroll
             for (int j = 0; j < kCols; ++j) hv[i][j] = (tx + j < g.TX) ? hp[j] : 0.f;
         }
@@ -149,7 +150,7 @@ hupd_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ V, const f
         if (m >= g.M) continue;
         const long long cidx = ((long long)n * g.M + m) * tvol + tin;        // contiguous [n, m, T] tensors
         if (H) {
-            float *hp = H + n * g.hsn + m * g.hsm + tin;
+            float *hp = H + n * g.hsn + m * g.hsm + tin_h;
             float gi[kCols], gs[kCols];
 #pragma unroll
             for (int j = 0; j < kCols; ++j) {

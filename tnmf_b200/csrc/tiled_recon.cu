@@ -50,7 +50,7 @@ recon_kernel(const Geo2 g, const TilePlan p, const float *__restrict__ W, const 
     auto issue = [&](int stage, int m) {
         float *tile = smem + stage * p.stage_floats;
         float *wf = tile + p.plane_floats;
-        stage_plane(tile, p.pitch, H + n * g.hsn + m * g.hsm, g.TY, g.TX, gy0, gx0, p.HR, p.WT, g.wrap, warp,
+        stage_plane(tile, p.pitch, H + n * g.hsn + m * g.hsm, g.TY, g.TX, g.hsy, gy0, gx0, p.HR, p.WT, g.wrap, warp,
                     n_warps, lane);
         // flipped atom slice, zero-padded at the end: wf[by][bx/4][c][bx%4] = W[m][c0+c][AY-1-by][AX-1-bx]
         const int qpr = AXP >> 2;
