@@ -29,7 +29,7 @@ using tiled::Geo2;
 using tiled::kCols;
 
 constexpr int kLX = 4, kLY = 8;          // lanes of a warp: 4 along x (8 columns each) x 8 along y
-constexpr int kConsumersMax = 12;
+constexpr int kConsumersMax = 12;     // consumer warps of a CTA (+ 1 producer warp = 416 threads, <= 152 registers)
 constexpr int kMaxSmem = 224 * 1024;
 
 // ---- device: mbarrier / TMA primitives (PTX ISA 8.x, sm_90+) ----------------------------------------------------
@@ -59,6 +59,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "TNMF_DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity)
         : "memory");
+}
+// Producer-side wait: the ring gives the producer several stage periods of slack, so it polls at a low rate instead
+// of competing with the consumer warps of its scheduler for issue slots.
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long *bar, unsigned parity) {
+    while (!mbar_try_wait(bar, parity)) __nanosleep(256);
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, unsigned long long *bar, int c0, int c1,
                                             int c2) {
@@ -116,6 +134,7 @@ struct HupdPlan {
     int WX, WY, consumers;        // consumer warps of a CTA: WX x WY, each 32 columns x 8 rows
     int tile_y, tile_x, tiles_y, tiles_x;
     int HR, pitch;                // staged rows, row pitch (floats)
+    int wide;                     // 1: the 9-warp / 224-register build of the kernel (hupd_needs_wide)
     int x_shift;                  // tile origin along x: -3..0, makes the TMA box start a multiple of 4 elements
     int plane_floats, taps_floats, stage_floats, n_stages;
     long long units;              // (sample, tile, atom block)
@@ -152,6 +171,8 @@ struct GradWPlan {
     size_t smem;
 };
 
+// accumulators 16*MB + two windows 2*(8+AXC) + ~30 for taps and addressing: beyond ~136 the 128-register build spills
+constexpr int hupd_needs_wide(int axc, int mb) { return 16 * mb + 2 * (kCols + axc) + 30 > 136 ? 1 : 0; }
 bool make_hupd_plan(const Geo2 &g, HupdPlan &p);
 bool make_recon_plan(const Geo2 &g, ReconPlan &p);
 bool make_gradw_plan(const Geo2 &g, GradWPlan &p);

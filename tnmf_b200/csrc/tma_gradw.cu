@@ -95,7 +95,7 @@ gradw_tma_kernel(const Geo2 g, const GradWPlan p, const __grid_constant__ CUtens
             Cursor cur = decode(pos0);
             const int g0y = g.offy - (g.AY - 1), g0x = g.offx - (g.AX - 1);
             for (long long pos = pos0; pos < pos1; ++pos) {
-                mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u);
+                mbar_wait_relaxed(&empty_bar[ring.stage], ring.phase ^ 1u);
                 float *sx = smem + (size_t)ring.stage * p.stage_floats;
                 float *sh = sx + p.x_floats;
                 const int y_base = cur.yc * p.RY, x_base = cur.xc * p.XC;

@@ -22,8 +22,11 @@
 namespace tnmf {
 namespace tma {
 
-template <int AXC, int DROP, int MB>
-__global__ void __launch_bounds__(32 * 9, 1)
+// WIDE = 1: at most 8 consumer warps + the producer (9 warps, up to 224 registers) for the register-hungry
+// combinations; WIDE = 0: up to 12 consumer warps + the producer (13 warps: 128 registers, the register file of an
+// SM sub-partition divided by the 4 warps one of the schedulers then hosts).
+template <int AXC, int DROP, int MB, int WIDE>
+__global__ void __launch_bounds__(WIDE ? 32 * 9 : 32 * (kConsumersMax + 1), 1)
 hupd_tma_kernel(const Geo2 g, const HupdPlan p, const __grid_constant__ CUtensorMap mapV,
                 const __grid_constant__ CUtensorMap mapR, const HupdArgs a) {
     extern __shared__ __align__(128) float smem[];
@@ -59,7 +62,7 @@ hupd_tma_kernel(const Geo2 g, const HupdPlan p, const __grid_constant__ CUtensor
                 // x0 = tx_i*tile_x + x_shift is congruent to offx mod 4, so the box starts on a multiple of 4
                 const int gx0 = tx_i * p.tile_x + p.x_shift - g.offx, gy0 = ty_i * p.tile_y - g.offy;
                 for (int c = 0; c < g.C; ++c) {
-                    mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u);
+                    mbar_wait_relaxed(&empty_bar[ring.stage], ring.phase ^ 1u);
                     float *sv = smem + (size_t)ring.stage * p.stage_floats;
                     float *sr = sv + p.plane_floats;
                     float *sw = sr + p.plane_floats;
@@ -105,6 +108,8 @@ hupd_tma_kernel(const Geo2 g, const HupdPlan p, const __grid_constant__ CUtensor
                                                                     2 * p.plane_floats);
                 for (int ay = 0; ay < g.AY; ++ay) {
                     for (int k = 0; k < NK; ++k) {
+                        // both windows live at once so that every tap quad is loaded once and feeds neg and pos
+                        // (measured on cfg2: 7% faster than one window at a time, even where it spills a few words)
                         float wv[kCols + AXC], wr[kCols + AXC];
 #pragma unroll
                         for (int q = 0; q < (kCols + AXC) / 4; ++q) {
@@ -155,38 +160,34 @@ hupd_tma_kernel(const Geo2 g, const HupdPlan p, const __grid_constant__ CUtensor
         const long long tin = (long long)ty * g.TX + tx;          // neg / pos / G / Gsum are dense
         const bool whole = tx >= 0 && tx + kCols <= g.TX;
         if (a.H) {
-            float hv[MB][kCols];
-#pragma unroll
-            for (int i = 0; i < MB; ++i) {                            // all H loads in flight before the first use
-                const float *hp = a.H + n * g.hsn + (m0 + i < g.M ? m0 + i : m0) * g.hsm + tin_h;
-                const unsigned mis = (unsigned)(reinterpret_cast<unsigned long long>(hp) & 15ull);
-                if (whole && mis == 0) {
-                    const float4 h0 = *reinterpret_cast<const float4 *>(hp);
-                    const float4 h1 = *reinterpret_cast<const float4 *>(hp + 4);
-                    hv[i][0] = h0.x; hv[i][1] = h0.y; hv[i][2] = h0.z; hv[i][3] = h0.w;
-                    hv[i][4] = h1.x; hv[i][5] = h1.y; hv[i][6] = h1.z; hv[i][7] = h1.w;
-                } else if (whole && mis == 8) {
-#pragma unroll
-                    for (int j = 0; j < kCols; j += 2) {
-                        const float2 h2 = *reinterpret_cast<const float2 *>(hp + j);
-                        hv[i][j] = h2.x; hv[i][j + 1] = h2.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < kCols; ++j) hv[i][j] = ((unsigned)(tx + j) < (unsigned)g.TX) ? hp[j] : 0.f;
-                }
-            }
 #pragma unroll
             for (int i = 0; i < MB; ++i) {
                 const int m = m0 + i;
                 if (m >= g.M) continue;
                 float *hp = a.H + n * g.hsn + m * g.hsm + tin_h;
+                const unsigned mis = (unsigned)(reinterpret_cast<unsigned long long>(hp) & 15ull);
+                float hv[kCols];
+                if (whole && mis == 0) {
+                    const float4 h0 = *reinterpret_cast<const float4 *>(hp);
+                    const float4 h1 = *reinterpret_cast<const float4 *>(hp + 4);
+                    hv[0] = h0.x; hv[1] = h0.y; hv[2] = h0.z; hv[3] = h0.w;
+                    hv[4] = h1.x; hv[5] = h1.y; hv[6] = h1.z; hv[7] = h1.w;
+                } else if (whole && mis == 8) {
+#pragma unroll
+                    for (int j = 0; j < kCols; j += 2) {
+                        const float2 h2 = *reinterpret_cast<const float2 *>(hp + j);
+                        hv[j] = h2.x; hv[j + 1] = h2.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kCols; ++j) hv[j] = ((unsigned)(tx + j) < (unsigned)g.TX) ? hp[j] : 0.f;
+                }
                 const long long cidx = ((long long)n * g.M + m) * tvol + tin;
                 float out[kCols];
 #pragma unroll
                 for (int j = 0; j < kCols; ++j) {
                     const bool ok = (unsigned)(tx + j) < (unsigned)g.TX;
-                    const float h = hv[i][j];
+                    const float h = hv[j];
                     float ps = pos[i][j];
                     if (a.G) {
                         const float gi = ok ? a.G[cidx + j] : 0.f;
@@ -201,7 +202,6 @@ hupd_tma_kernel(const Geo2 g, const HupdPlan p, const __grid_constant__ CUtensor
                     hn /= ps;
                     out[j] = hn;
                 }
-                const unsigned mis = (unsigned)(reinterpret_cast<unsigned long long>(hp) & 15ull);
                 if (whole && mis == 0) {
                     *reinterpret_cast<float4 *>(hp) = make_float4(out[0], out[1], out[2], out[3]);
                     *reinterpret_cast<float4 *>(hp + 4) = make_float4(out[4], out[5], out[6], out[7]);
@@ -231,10 +231,10 @@ hupd_tma_kernel(const Geo2 g, const HupdPlan p, const __grid_constant__ CUtensor
     }
 }
 
-template <int AXC, int DROP, int MB>
+template <int AXC, int DROP, int MB, int WIDE>
 static int launch_one(const Geo2 &g, const HupdPlan &p, const CUtensorMap &mapV, const CUtensorMap &mapR,
                       const HupdArgs &a, cudaStream_t st) {
-    auto kern = hupd_tma_kernel<AXC, DROP, MB>;
+    auto kern = hupd_tma_kernel<AXC, DROP, MB, WIDE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     if (e != cudaSuccess) return status_from_cuda(e);
     kern<<<(unsigned)p.grid, p.threads, p.smem, st>>>(g, p, mapV, mapR, a);
@@ -246,9 +246,9 @@ template <>
 int hupd_launch_axc<TNMF_AXC>(const Geo2 &g, const HupdPlan &p, const CUtensorMap &mapV, const CUtensorMap &mapR,
                               const HupdArgs &a, cudaStream_t st) {
 #define TNMF_HUPD_CASE(mb)                                                                         \
-    if (p.MB == mb)                                                                                \
-        return p.ch.drop ? launch_one<TNMF_AXC, 1, mb>(g, p, mapV, mapR, a, st)                    \
-                         : launch_one<TNMF_AXC, 0, mb>(g, p, mapV, mapR, a, st);
+    if (p.MB == mb && p.wide == hupd_needs_wide(TNMF_AXC, mb))                                     \
+        return p.ch.drop ? launch_one<TNMF_AXC, 1, mb, hupd_needs_wide(TNMF_AXC, mb)>(g, p, mapV, mapR, a, st)  \
+                         : launch_one<TNMF_AXC, 0, mb, hupd_needs_wide(TNMF_AXC, mb)>(g, p, mapV, mapR, a, st);
     TNMF_HUPD_CASE(1)
     TNMF_HUPD_CASE(2)
     TNMF_HUPD_CASE(3)

@@ -69,40 +69,58 @@ int sm_count() {
 }
 
 // ---- plans -----------------------------------------------------------------------------------------------------------
-// CTA shape shared by the two position-tiled kernels: up to 8 consumer warps arranged WX x WY, each covering
-// 32 columns x (8*RB) rows; the arrangement with the smallest staged area (halo included) plus idle-lane penalty wins.
+// CTA shape shared by the two position-tiled kernels: WX x WY consumer warps (at most 12), each covering 32 columns x
+// (8*RB) rows.  Cost model: a tile keeps its SM busy for max(active warps, 8) warp-tile periods (fewer than 8 active
+// warps cannot hide the LDS latency of the FFMA stream), plus a small charge for the staged bytes (halo included).
 template <typename Plan>
-static bool finish_tile_plan(Plan &p, int EY, int EX_in, int AY, int RB, int planes, int taps_floats, int x_shift = 0) {
+static bool finish_tile_plan(Plan &p, int EY, int EX_in, int AY, int RB, int planes, int taps_floats, int x_shift = 0,
+                             int max_consumers = kConsumersMax) {
     const int EX = EX_in - x_shift;                               // columns to cover when the origin is shifted left
     const int AXP = p.ch.AXP;
     const int wtile_y = kLY * RB, wtile_x = kLX * kCols;
     const int need_wy = ceil_div(EY, wtile_y), need_wx = ceil_div(EX, wtile_x);
-    long long best_cost = -1;
+    int force_wx = 0, force_wy = 0;
+    if (const char *e = getenv("TNMF_TMA_WX")) force_wx = atoi(e);
+    if (const char *e = getenv("TNMF_TMA_WY")) force_wy = atoi(e);
+    double best_cost = -1;
     Plan best = p;
-    for (int wx = 1; wx <= 8; wx <<= 1) {
-        Plan q = p;
-        q.WX = wx < need_wx ? wx : need_wx;
-        q.WY = 8 / wx < need_wy ? 8 / wx : need_wy;
-        q.consumers = q.WX * q.WY;
-        q.tile_y = q.WY * wtile_y;
-        q.tile_x = q.WX * wtile_x;
-        q.tiles_y = ceil_div(EY, q.tile_y);
-        q.tiles_x = ceil_div(EX, q.tile_x);
-        q.HR = q.tile_y + AY - 1;
-        q.pitch = odd_pitch(q.tile_x + AXP);
-        if (q.pitch > 256 || q.HR > 256) continue;                // TMA box limits
-        q.plane_floats = round_up(q.HR * q.pitch, 32);
-        q.taps_floats = round_up(taps_floats, 32);
-        q.stage_floats = planes * q.plane_floats + q.taps_floats;
-        const size_t stage_bytes = (size_t)q.stage_floats * sizeof(float);
-        q.n_stages = (int)(kMaxSmem / stage_bytes);
-        if (q.n_stages > 6) q.n_stages = 6;
-        if (q.n_stages < 2) continue;
-        q.smem = (size_t)q.n_stages * stage_bytes;
-        const long long staged = (long long)q.tiles_y * q.tiles_x * q.HR * q.pitch;
-        const long long slots = (long long)q.tiles_y * q.tiles_x * q.WX * q.WY * wtile_y * wtile_x;
-        const long long cost = staged + 8 * (slots - (long long)EY * EX_in) + (q.n_stages < 3 ? staged : 0);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = q; }
+    for (int wx = 1; wx <= max_consumers && wx <= need_wx; ++wx) {
+        for (int wy = 1; wx * wy <= max_consumers && wy <= need_wy; ++wy) {
+            if (force_wx && force_wy && (wx != (force_wx < need_wx ? force_wx : need_wx) ||
+                                         wy != (force_wy < need_wy ? force_wy : need_wy)))
+                continue;
+            // warps are dealt round-robin to the 4 schedulers of an SM: a consumer count that is not a multiple of 4
+            // leaves one scheduler with an extra warp and everyone waits for it (measured: 3x3 warps 30% slower)
+            if (!(force_wx && force_wy) && (wx * wy) % 4 != 0 && (wx < need_wx || wy < need_wy)) continue;
+            Plan q = p;
+            q.WX = wx;
+            q.WY = wy;
+            q.consumers = wx * wy;
+            q.tile_y = wy * wtile_y;
+            q.tile_x = wx * wtile_x;
+            q.tiles_y = ceil_div(EY, q.tile_y);
+            q.tiles_x = ceil_div(EX, q.tile_x);
+            q.HR = q.tile_y + AY - 1;
+            q.pitch = odd_pitch(q.tile_x + AXP);
+            if (q.pitch > 256 || q.HR > 256) continue;            // TMA box limits
+            q.plane_floats = round_up(q.HR * q.pitch, 32);
+            q.taps_floats = round_up(taps_floats, 32);
+            q.stage_floats = planes * q.plane_floats + q.taps_floats;
+            const size_t stage_bytes = (size_t)q.stage_floats * sizeof(float);
+            q.n_stages = (int)(kMaxSmem / stage_bytes);
+            if (q.n_stages > 6) q.n_stages = 6;
+            if (q.n_stages < 2) continue;
+            q.smem = (size_t)q.n_stages * stage_bytes;
+            // active warps of the last tile column / row
+            const int last_wx = need_wx - (q.tiles_x - 1) * wx, last_wy = need_wy - (q.tiles_y - 1) * wy;
+            auto busy = [](int active) { return active < 8 ? 8 : active; };
+            double periods = (double)(q.tiles_x - 1) * (q.tiles_y - 1) * busy(wx * wy) +
+                             (double)(q.tiles_y - 1) * busy(last_wx * wy) + (double)(q.tiles_x - 1) * busy(wx * last_wy) +
+                             busy(last_wx * last_wy);
+            const double staged = (double)q.tiles_y * q.tiles_x * q.HR * q.pitch / ((double)EY * EX);   // ~1.3 .. 3
+            const double cost = periods * (1.0 + 0.02 * staged) * (q.n_stages < 3 ? 1.15 : 1.0);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = q; }
+        }
     }
     if (best_cost < 0) return false;
     p = best;
@@ -118,7 +136,9 @@ bool make_hupd_plan(const Geo2 &g, HupdPlan &p) {
     p.nblk = nmb;
     // box origin = x0 - offx must be a multiple of 4 elements: start the tile grid at x_shift = offx mod 4 (- 4)
     p.x_shift = (g.offx & 3) ? (g.offx & 3) - 4 : 0;
-    if (!finish_tile_plan(p, g.TY, g.TX, g.AY, 1, 2, g.AY * p.ch.AXP * p.MB, p.x_shift)) return false;
+    p.wide = hupd_needs_wide(p.ch.AXC, p.MB);
+    if (!finish_tile_plan(p, g.TY, g.TX, g.AY, 1, 2, g.AY * p.ch.AXP * p.MB, p.x_shift, p.wide ? 8 : kConsumersMax))
+        return false;
     p.units = (long long)g.N * p.tiles_y * p.tiles_x * p.nblk;
     if (p.units <= 0 || p.units >= 0x7fffffffLL) return false;
     p.grid = (int)(p.units < sm_count() ? p.units : sm_count());

@@ -19,7 +19,7 @@ namespace tnmf {
 namespace tma {
 
 template <int AXC, int DROP, int CB, int RB>
-__global__ void __launch_bounds__(32 * 9, 1)
+__global__ void __launch_bounds__(32 * (kConsumersMax + 1), 1)
 recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtensorMap mapH, const ReconArgs a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long full_bar[8], empty_bar[8];
@@ -53,7 +53,7 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
                 const int tx_i = r % p.tiles_x, ty_i = r / p.tiles_x;
                 const int gx0 = tx_i * p.tile_x + g.offx - (g.AX - 1), gy0 = ty_i * p.tile_y + g.offy - (g.AY - 1);
                 for (int m = 0; m < g.M; ++m) {
-                    mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u);
+                    mbar_wait_relaxed(&empty_bar[ring.stage], ring.phase ^ 1u);
                     float *sh = smem + (size_t)ring.stage * p.stage_floats;
                     float *sw = sh + p.plane_floats;
                     mbar_arrive_expect_tx(&full_bar[ring.stage], stage_bytes);
