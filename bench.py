@@ -13,10 +13,12 @@ reference) over a synthetic batch.  The metric is BASELINE.json's: sample-iterat
     initialisation, K iterations, download of W and of the energy, all inside the timed region.
     N > 1 (torchrun, one rank per GPU): weak scaling - every rank owns a batch of the workload's size, the only
     collective is the all-reduce of the stacked W-gradient numerator/denominator each iteration.
-  * reference arm (`--impl reference`): the CPU restatement of the reference's numpy backend (oracle/, numpy on
-    the host cores) on a bounded sample of the same workload.  /root/reference is a pure-Python package that does
-    not travel to the GPU box, so the oracle port - pinned to the reference's golden vectors - is the timed CPU
-    implementation.
+  * reference arm (`--impl reference`): the CPU restatement of the reference's algorithm (oracle/) on a bounded
+    sample of the same workload, on all host cores: the Fourier-domain form of the reference's default
+    numpy_fft / numpy_caching_fft backends (scipy.fft with workers=-1, exactly the reference's threading), with the
+    coordinate-space form of its `numpy` backend timed beside it.  /root/reference is a pure-Python package that
+    does not travel to the GPU box, so the oracle port - pinned to the reference's golden vectors - is the timed
+    CPU implementation.
 
 One JSON line on stdout (rank 0).
 """
@@ -46,7 +48,7 @@ WORKLOADS = {
     'cfg4': dict(N=2048, C=1, D=(4096,), M=64, A=(128,), text='1-D signals: 2048 x 1x4096 per GPU, 64 atoms x 128'),
     'cfg5': dict(N=16, C=1, D=(512, 512), M=8, A=(64, 64), text='large-atom 2-D: 16 x 1x512x512, 8 atoms 1x64x64'),
 }
-CPU_SAMPLE = {'cfg1': 100, 'cfg2': 2, 'cfg3': 4, 'cfg4': 64, 'cfg5': 1}   # samples of the bounded CPU run
+CPU_SAMPLE = {'cfg1': 100, 'cfg2': 4, 'cfg3': 16, 'cfg4': 64, 'cfg5': 1}   # samples of the bounded CPU run
 
 
 def flops_per_sample_iteration(w):
@@ -119,13 +121,14 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference's numpy backend on a bounded sample
 # -------------------------------------------------------------------------------------------------------------
-def cpu_oracle_run(w, n_sample, steps, warmup):
-    """Times OracleNMF's MU iteration (oracle/tnmf_oracle.py) on `n_sample` samples of workload `w`.
+def cpu_oracle_run(w, n_sample, steps, warmup, fourier=True):
+    """Times the MU iteration of the CPU oracle (oracle/tnmf_oracle.py) on `n_sample` samples of workload `w`:
+    OracleNMF_FFT (Fourier-domain form, scipy.fft on all host threads) or OracleNMF (coordinate-space form).
     Returns (sample-iterations/s, seconds per step)."""
     from oracle import tnmf_oracle as orc
     rng = np.random.default_rng(0)
     V = rng.random((n_sample, w['C'], *w['D']), dtype=np.float32)
-    nmf = orc.OracleNMF(n_atoms=w['M'], atom_shape=w['A'])
+    nmf = (orc.OracleNMF_FFT if fourier else orc.OracleNMF)(n_atoms=w['M'], atom_shape=w['A'])
     np.random.seed(0)
     nmf.initialize(V)
     for _ in range(warmup):
@@ -144,17 +147,22 @@ def run_reference(args, w):
     if rank != 0:
         return
     n_sample = CPU_SAMPLE[args.workload]
-    value, s_per_step = cpu_oracle_run(w, n_sample, args.steps, args.warmup)
+    value, s_per_step = cpu_oracle_run(w, n_sample, args.steps, args.warmup, fourier=True)
+    n_direct = max(1, n_sample // 2)
+    direct_value, _ = cpu_oracle_run(w, n_direct, 1, 1, fourier=False)
     sample = f'{n_sample} of {w["N"]} samples of {args.workload}, every step one full MU iteration'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * s_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
         'config': {'workload': f'{args.workload}: {w["text"]}', 'algorithm': 'batch MU', 'cpu_sample': sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'sample': sample,
-                         'host_cores': os.cpu_count(),
-                         'note': 'oracle/tnmf_oracle.py (numpy restatement of the reference numpy backend); the '
-                                 'einsum it uses is single-threaded'},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample,
+                         'what': 'oracle.OracleNMF_FFT: Fourier-domain restatement of the reference numpy_fft / '
+                                 'numpy_caching_fft backends, scipy.fft workers=-1 (all host threads)',
+                         'numpy_direct': {'value': direct_value, 'unit': UNIT, 'cores': 1,
+                                          'sample': f'{n_direct} samples, 1 warm-up + 1 timed iteration',
+                                          'what': 'oracle.OracleNMF: coordinate-space restatement of the reference '
+                                                  'numpy backend (single-threaded shift-and-add)'}},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -317,10 +325,17 @@ def run_b200(args, w):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_sample = CPU_SAMPLE[args.workload]
-        cpu_value, _ = cpu_oracle_run(w, n_sample, 2, 1)
-        cpu = {'value': cpu_value, 'unit': UNIT, 'cores': 1, 'kind': 'port', 'host_cores': os.cpu_count(),
-               'sample': f'{n_sample} of {w["N"]} samples of {args.workload}, 1 warm-up + 2 timed MU iterations of '
-                         f'oracle/tnmf_oracle.py (numpy restatement of the reference numpy backend)'}
+        cpu_value, _ = cpu_oracle_run(w, n_sample, 3, 1, fourier=True)
+        n_direct = max(1, n_sample // 2)
+        direct_value, _ = cpu_oracle_run(w, n_direct, 1, 1, fourier=False)
+        cpu = {'value': cpu_value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+               'sample': f'{n_sample} of {w["N"]} samples of {args.workload}, 1 warm-up + 3 timed MU iterations',
+               'what': 'oracle.OracleNMF_FFT: Fourier-domain restatement of the reference numpy_fft / '
+                       'numpy_caching_fft backends, scipy.fft workers=-1 (all host threads)',
+               'numpy_direct': {'value': direct_value, 'unit': UNIT, 'cores': 1,
+                                'sample': f'{n_direct} samples, 1 warm-up + 1 timed iteration',
+                                'what': 'oracle.OracleNMF: coordinate-space restatement of the reference numpy '
+                                        'backend (single-threaded shift-and-add)'}}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,

@@ -410,3 +410,92 @@ class OracleNMF:
         if 'batch_size' in kwargs or 'algorithm' in kwargs:
             return self.fit_minibatches(V, **kwargs)
         return self.fit_batch(V, **kwargs)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fourier-domain restatement ('valid' mode): the algorithm of the reference's numpy_fft / numpy_caching_fft
+# backends, used as the multi-threaded CPU baseline of bench.py (scipy.fft with workers=-1, like the reference)
+# ---------------------------------------------------------------------------------------------------
+def _fft_plan(sample_shape: Sequence[int], atom_shape: Sequence[int]):
+    """Transform lengths: next_fast_len(D + T - 1) per shift axis.  Follows tnmf/backends/_NumPyFFTBackend.py:43."""
+    from scipy.fft import next_fast_len
+    t_shape = transform_shape('valid', sample_shape, atom_shape)
+    return tuple(int(next_fast_len(int(d) + int(t) - 1)) for d, t in zip(sample_shape, t_shape))
+
+
+def fft_reconstruct(W: np.ndarray, H: np.ndarray) -> np.ndarray:
+    """R = sum_m H[:, m] (*) W[m] cropped to the sample ('valid' mode), evaluated as a product of spectra summed
+    over the atoms.  Follows tnmf/backends/NumPy_FFT.py:16-40,90-93 and _NumPyFFTBackend.py:49-60."""
+    from scipy.fft import irfftn, rfftn
+    k = W.ndim - 2
+    axes = tuple(range(-k, 0))
+    atom_shape = W.shape[2:]
+    sample_shape = tuple(t - a + 1 for t, a in zip(H.shape[2:], atom_shape))
+    shape = _fft_plan(sample_shape, atom_shape)
+    Hf = rfftn(H, s=shape, axes=axes, workers=-1)
+    Wf = rfftn(W, s=shape, axes=axes, workers=-1)
+    Rf = np.einsum('nm...,mc...->nc...', Hf, Wf, optimize=True)
+    full = irfftn(Rf, s=shape, axes=axes, workers=-1)
+    crop = (slice(None), slice(None)) + tuple(slice(a - 1, a - 1 + d) for a, d in zip(atom_shape, sample_shape))
+    return np.ascontiguousarray(full[crop]).astype(H.dtype, copy=False)
+
+
+def _fft_correlate(X: np.ndarray, Y: np.ndarray, contraction: str, out_shape: Sequence[int], shift: Sequence[int],
+                   shape: Sequence[int]) -> np.ndarray:
+    """c[k] = sum_d X[d] * Y[d + k] for k = shift_i .. shift_i + out_shape_i - 1 (circular indices), contracted over
+    the labelled axes in Fourier space: conj(X^) * Y^.  Follows the 'correlate' branch of
+    tnmf/backends/NumPy_FFT.py:28-29 (flip == conjugate spectrum up to a shift)."""
+    from scipy.fft import irfftn, rfftn
+    k = len(shape)
+    axes = tuple(range(-k, 0))
+    Xf = rfftn(X, s=shape, axes=axes, workers=-1)
+    Yf = rfftn(Y, s=shape, axes=axes, workers=-1)
+    Cf = np.einsum(contraction, np.conj(Xf), Yf, optimize=True)
+    c = irfftn(Cf, s=shape, axes=axes, workers=-1)
+    for ax, (s0, n, L) in enumerate(zip(shift, out_shape, shape)):
+        idx = (np.arange(s0, s0 + n) % L)
+        c = np.take(c, idx, axis=ax + 2)
+    return c
+
+
+def fft_gradient_H(V: np.ndarray, W: np.ndarray, H: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """neg/pos[n,m,t] = sum_c sum_a W[m,c,a] * X[n,c,t-p+a], X = V / R.  Follows tnmf/backends/NumPy_FFT.py:71-88."""
+    atom_shape, sample_shape = W.shape[2:], V.shape[2:]
+    shape = _fft_plan(sample_shape, atom_shape)
+    R = fft_reconstruct(W, H)
+    shift = tuple(-(a - 1) for a in atom_shape)
+    out = []
+    for X in (V, R):
+        out.append(_fft_correlate(W, X, 'mc...,nc...->nm...', H.shape[2:], shift, shape).astype(H.dtype, copy=False))
+    return out[0], out[1]
+
+
+def fft_gradient_W(V: np.ndarray, W: np.ndarray, H: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """neg/pos[m,c,a] = sum_n sum_d H[n,m,d+p-a] * X[n,c,d].  Follows tnmf/backends/NumPy_FFT.py:52-69."""
+    atom_shape, sample_shape = W.shape[2:], V.shape[2:]
+    shape = _fft_plan(sample_shape, atom_shape)
+    R = fft_reconstruct(W, H)
+    out = []
+    for X in (V, R):
+        g = _fft_correlate(X, H, 'nc...,nm...->mc...', atom_shape, (0,) * len(atom_shape), shape)   # g[k], k = p - a
+        out.append(np.ascontiguousarray(np.flip(g, axis=tuple(range(2, g.ndim)))).astype(W.dtype, copy=False))
+    return out[0], out[1]
+
+
+class OracleNMF_FFT(OracleNMF):
+    """The iteration of OracleNMF with the three contractions evaluated in Fourier space ('valid' mode only)."""
+
+    def __init__(self, n_atoms: int, atom_shape: Sequence[int], inhibition_range=None):
+        super().__init__(n_atoms, atom_shape, inhibition_range, 'valid')
+
+    def energy(self):
+        return 0.5 * np.sum(np.square(self.V - fft_reconstruct(self.W, self.H)))
+
+    def update_H(self, s=slice(None), sparsity=0.0, inhibition=0.0, cross_inhibition=0.0) -> None:
+        assert inhibition == 0 and cross_inhibition == 0, 'the FFT restatement times the plain MU iteration only'
+        Hs = self.H[s]
+        neg, pos = fft_gradient_H(self.V[s], self.W, Hs)
+        multiplicative_update(Hs, neg, pos, sparsity=sparsity)
+
+    def gradient_W(self, s=slice(None)):
+        return fft_gradient_W(self.V[s], self.W, self.H[s])

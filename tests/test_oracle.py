@@ -151,3 +151,34 @@ def test_unknown_mode_raises():
         orc.transform_shape('reflect', (8,), (3,))
     with pytest.raises(ValueError):
         orc.OracleNMF(2, (3,), reconstruction_mode='same')
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the Fourier-domain restatement (CPU baseline of bench.py) against the coordinate-space oracle
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('shape', [((3, 2, 4), (20,), (5,)), ((2, 3, 4), (24, 17), (5, 4)), ((2, 1, 2), (6, 7, 5), (2, 3, 2))])
+def test_fft_restatement_matches_direct(shape):
+    (N, C, M), D, A = shape
+    rng = np.random.default_rng(11)
+    V = rng.random((N, C) + D)
+    W = rng.random((M, C) + A)
+    H = rng.random((N, M) + orc.transform_shape('valid', D, A))
+    assert np.allclose(orc.fft_reconstruct(W, H), orc.reconstruct(W, H), rtol=1e-10, atol=1e-12)
+    for a, b in zip(orc.fft_gradient_H(V, W, H), orc.reconstruction_gradient_H(V, W, H)):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-11)
+    for a, b in zip(orc.fft_gradient_W(V, W, H), orc.reconstruction_gradient_W(V, W, H)):
+        assert np.allclose(a, b, rtol=1e-10, atol=1e-11)
+
+
+def test_fft_restatement_fit_follows_direct_fit():
+    rng = np.random.default_rng(12)
+    V = rng.random((3, 2, 16, 12))
+    fits = []
+    for cls in (orc.OracleNMF, orc.OracleNMF_FFT):
+        np.random.seed(4)
+        nmf = cls(3, (4, 3))
+        nmf.fit_batch(V, n_iterations=8, sparsity_H=0.1)
+        fits.append(nmf)
+    assert np.isclose(fits[0].energy(), fits[1].energy(), rtol=1e-9)
+    assert np.allclose(fits[0].W, fits[1].W, rtol=1e-8, atol=1e-12)
+    assert np.allclose(fits[0].H, fits[1].H, rtol=1e-7, atol=1e-12)
