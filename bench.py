@@ -307,9 +307,18 @@ def run_b200(args, w):
     step_ms = ms_total / args.steps
     flops_step = flops_per_sample_iteration(w) * n_local
     bytes_step = hbm_bytes_per_sample_iteration(w) * n_local
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            entry = json.load(f).get(args.workload, {}).get(dominant)
+        if entry and entry.get('family') == be.kernel_families().get(dominant):
+            traffic, traffic_src = entry['bytes'], entry['source']
+    except (OSError, ValueError):
+        pass
     roofline = {
         'bound': 'fp32', 'kernel': dominant, 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-        'frac': (achieved / fp32_peak) if fp32_peak else None, 'traffic': None,
+        'frac': (achieved / fp32_peak) if fp32_peak else None, 'traffic': traffic, 'traffic_source': traffic_src,
+        'traffic_unit': 'bytes per launch (dram read + write, ncu)',
         'peak_source': 'FP32-FMA probe kernel of libtnmf_b200.so timed in this run (MEASURED_PEAKS.json holds no '
                        'FP32 figure); nominal 148 SM x 128 FMA x 2 x 1.965 GHz = 74.4',
         'kernel_ms': kern_ms, 'kernel_launches_per_step': kern_calls,
