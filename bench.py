@@ -375,7 +375,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
-    ap.add_argument('--kernel-path', default='auto', choices=['auto', 'generic', 'tiled', 'tma'])
+    ap.add_argument('--kernel-path', default='auto', choices=['auto', 'generic', 'tiled', 'tma', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

@@ -298,7 +298,8 @@ TMA_CASES = [
 
 @pytest.mark.parametrize('mode', ('valid', 'full'))
 @pytest.mark.parametrize('case', range(len(TMA_CASES)))
-def test_tma_vs_oracle(case, mode):
+def test_tma_vs_oracle(case, mode, monkeypatch):
+    monkeypatch.setenv('TNMF_NO_TC', '1')       # 'auto' without the tensor-core H update: this test pins the FP32 kernels
     N, C, M, D, A = TMA_CASES[case]
     rng = np.random.default_rng(200 + case)
     V = rng.random((N, C) + D).astype(np.float32)
@@ -336,6 +337,55 @@ def test_tma_vs_oracle(case, mode):
     be.apply_W_update(Wd, be.gradient_W(V, Wd, Hd, slice(None), grad))
     _close(Wd, nmf.W, 5e-5)
     assert np.allclose(Wd.sum(dim=tuple(range(2, Wd.dim()))).cpu().numpy(), 1.0, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, 3xTF32) H gradient / fused H update against the oracle
+# ---------------------------------------------------------------------------------------------------------
+TC_CASES = [
+    # N, C, M, D, A
+    (3, 3, 16, (64, 64), (11, 11)),     # cfg2-like: K = 33 -> 40, one full atom block
+    (2, 1, 32, (40, 50), (15, 15)),     # cfg3-like: two atom blocks, tallest atom the TMEM ring takes
+    (5, 2, 9, (100, 36), (4, 9)),       # partial atom block, tall samples (many ring wrap-arounds)
+    (1, 1, 2, (30, 300), (5, 7)),       # K = 7 -> 8, columns of one sample span several tiles
+    (2, 3, 5, (20, 24), (3, 3)),
+    (4, 1, 1, (17, 16), (1, 1)),        # single atom of one pixel: every source row completes an output row
+    (2, 2, 3, (6, 8), (6, 8)),          # atom as large as the sample ('full': a single activation)
+    (40, 1, 4, (48, 500), (5, 5)),      # more tiles than SMs: several work units per CTA
+    (7, 2, 17, (31, 45), (2, 13)),      # 17 atoms = a full block + 1, even atom height
+]
+
+
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+@pytest.mark.parametrize('case', range(len(TC_CASES)))
+def test_tc_hupdate_vs_oracle(case, mode):
+    """3xTF32 products carry ~2^-21 relative error against FP32's 2^-24: single operations within 2e-5 of max|ref|
+    like the FP32 kernels, the fused update within 5e-5."""
+    N, C, M, D, A = TC_CASES[case]
+    rng = np.random.default_rng(300 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    be.reconstruct(Wd, Hd)
+    assert be.kernel_families()['update_h'] == 'tc'
+    neg, pos = be.reconstruction_gradient_H(V, Wd, Hd)
+    rn, rp = orc.reconstruction_gradient_H(V64, W64, H64, mode)
+    _close(neg, rn, 2e-5)
+    _close(pos, rp, 2e-5)
+    nmf = orc.OracleNMF(M, A, reconstruction_mode=mode)
+    nmf.V, nmf.W, nmf.H = V64, W64.copy(), H64.copy()
+    for s in (slice(0, 1), slice(1, N)):
+        nmf.update_H(s, sparsity=0.1, inhibition=0.2, cross_inhibition=0.3 if M > 1 else 0.0)
+        be.update_H(V, Wd, Hd, s, 0.1, 0.2, 0.3 if M > 1 else 0.0, nmf.inhibition_kernels)
+    _close(Hd, nmf.H, 5e-5)
+    # plain update (no regularisers), twice in a row: the second call reads what the first one wrote
+    nmf.update_H(slice(None))
+    be.update_H(V, Wd, Hd)
+    nmf.update_H(slice(None))
+    be.update_H(V, Wd, Hd)
+    _close(Hd, nmf.H, 1e-4)
 
 
 def test_empty_and_single_sample_batches():

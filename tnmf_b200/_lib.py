@@ -14,11 +14,11 @@ from typing import Optional, Sequence
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libtnmf_b200.so')
-SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu', 'tma_kernels.cu')
+SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu', 'tma_kernels.cu', 'tc_hupd.cu')
 # compiled once per atom-width chunk (-DTNMF_AXC=...): the register-tiled kernels
 CHUNKED_SOURCES = ('tiled_recon.cu', 'tiled_hupd.cu', 'tiled_gradw.cu', 'tma_recon.cu', 'tma_hupd.cu', 'tma_gradw.cu')
 CHUNKS = (4, 8, 12, 16)
-HEADERS = ('common.cuh', 'tiled_common.cuh', 'tma_common.cuh', os.path.join('..', '..', 'include', 'tnmf_b200.h'))
+HEADERS = ('common.cuh', 'tiled_common.cuh', 'tma_common.cuh', 'tc_common.cuh', os.path.join('..', '..', 'include', 'tnmf_b200.h'))
 
 # NB: no --use_fast_math: divisions must round like the reference's IEEE arithmetic.
 NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
@@ -26,7 +26,7 @@ NVCC_FLAGS = ('-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 
 TNMF_F32, TNMF_F64 = 0, 1
 MODES = {'valid': 0, 'full': 1, 'circular': 2}
-PATHS = {'auto': 0, 'generic': 1, 'tiled': 2, 'tma': 3}
+PATHS = {'auto': 0, 'generic': 1, 'tiled': 2, 'tma': 3, 'tc': 4}
 OP_RECONSTRUCT, OP_GRADIENT_H, OP_GRADIENT_W = 0, 1, 2
 TNMF_OK, TNMF_EINVAL, TNMF_EUNSUPPORTED, TNMF_EWORKSPACE, TNMF_ECUDA = 0, 1, 2, 3, 1000
 ABI_VERSION = 2

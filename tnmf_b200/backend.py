@@ -44,7 +44,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
     init : 'numpy' (default) draws H then W from the global legacy numpy RNG exactly like
         tnmf/backends/_Backend.py:83-98 (bit-identical seeded initialisation); 'device' draws them with the
         device RNG (for problem sizes whose float64 host draw would not fit host memory).
-    kernel_path : 'auto' | 'generic' | 'tiled'   (diagnostics; see include/tnmf_b200.h)
+    kernel_path : 'auto' | 'generic' | 'tiled' | 'tma' | 'tc'   (diagnostics; see include/tnmf_b200.h)
     """
 
     def __init__(self, reconstruction_mode: str = 'valid', device=None, init: str = 'numpy',
@@ -337,6 +337,8 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         fam = int(self._lib.tnmf_kernel_family(ctypes.byref(p), op))
         if op == _lib.OP_GRADIENT_W:
             return 2
+        if fam == _lib.PATHS['tc']:
+            return (p.n_atoms + 15) // 16        # one launch per block of 16 atoms
         return 2 if fam == _lib.PATHS['tma'] else 1
 
     def reconstruction_gradient_H(self, V, W, H, s: slice = sliceNone):

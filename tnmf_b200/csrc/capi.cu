@@ -1,6 +1,7 @@
 // extern "C" surface of libtnmf_b200.so: argument validation, geometry set-up and kernel-family dispatch.
 // See include/tnmf_b200.h for the contract of every entry point and the reference interface it replaces.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -39,13 +40,26 @@ int make_geo(const tnmf_problem *p, Geo &g) {
     return TNMF_OK;
 }
 
+// The tensor-core H update pads the contraction C*A_x to a multiple of 8 and the atoms to a multiple of 16; 'auto'
+// takes it when at least half of every MMA is useful work and the problem fills the 128-column tiles
+// (TNMF_NO_TC=1 in the environment keeps 'auto' on the FP32 kernels).
+bool tc_worthwhile(const Geo &g) {
+    if (getenv("TNMF_NO_TC")) return false;
+    const int k = g.C * g.A[2], kp = (k + 7) / 8 * 8, mp = (g.M + 15) / 16 * 16;
+    const double useful = ((double)k / kp) * ((double)g.M / mp);
+    return useful >= 0.5 && (long long)g.N * g.T[2] >= 128 && g.A[1] >= 3;
+}
+
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;
 // a forced family that cannot serve the problem is an error.
 int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
     *err = TNMF_OK;
     if (p->path == TNMF_PATH_GENERIC) return TNMF_PATH_GENERIC;
+    if (op == TNMF_OP_GRADIENT_H && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_worthwhile(g))) &&
+        tc_hupd_supported(g, p->dtype))
+        return TNMF_PATH_TC;
     bool tma_ok = false;
-    if (p->path == TNMF_PATH_AUTO || p->path == TNMF_PATH_TMA) {
+    if (p->path == TNMF_PATH_AUTO || p->path == TNMF_PATH_TMA || p->path == TNMF_PATH_TC) {
         if (op == TNMF_OP_RECONSTRUCT) tma_ok = tma_recon_supported(g, p->dtype);
         else if (op == TNMF_OP_GRADIENT_H) tma_ok = tma_hupd_supported(g, p->dtype);
         else tma_ok = tma_gradw_supported(g, p->dtype);
@@ -114,7 +128,7 @@ int tnmf_uses_tiled_path(const tnmf_problem *p) {
     if (make_geo(p, g)) return 0;
     int err;
     const int f = choose_family(p, g, TNMF_OP_GRADIENT_H, &err);
-    return (f == TNMF_PATH_TILED || f == TNMF_PATH_TMA) ? 1 : 0;
+    return (f == TNMF_PATH_TILED || f == TNMF_PATH_TMA || f == TNMF_PATH_TC) ? 1 : 0;
 }
 
 int tnmf_kernel_family(const tnmf_problem *p, int op) {
@@ -201,6 +215,9 @@ static int gradient_h_dispatch(const tnmf_problem *p, const void *V, const void 
     cudaStream_t st = (cudaStream_t)stream;
     int family = choose_family(p, g, TNMF_OP_GRADIENT_H, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TC)
+        return tc_gradient_h(g, (const float *)V, (const float *)R, (const float *)W, (float *)neg, (float *)pos,
+                             (float *)H, reg, (const float *)G, lambda, (const float *)Gsum, lambda_cross, st);
     if (family == TNMF_PATH_TMA && (!aligned16(V) || !aligned16(R) || !workspace)) {
         if (p->path == TNMF_PATH_TMA) return workspace ? TNMF_EUNSUPPORTED : TNMF_EWORKSPACE;
         family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;

@@ -1,0 +1,102 @@
+// tcgen05 / TMEM primitives for the tensor-core kernels (sm_100a), hand-written PTX.
+//
+// Operand layout used throughout: the canonical K-major, no-swizzle ("interleaved") shared-memory layout of the
+// tcgen05 matrix descriptors for 32-bit elements.  A matrix of `rows` x K floats is stored as 8-row x 16-byte core
+// matrices; element (i, k) lives at byte offset
+//       (i / 8) * 128  +  (k / 4) * (rows * 16)  +  (i % 8) * 16  +  (k % 4) * 4
+// i.e. stride-byte-offset (between 8-row groups) = 128 and leading-byte-offset (between the 16-byte K chunks) =
+// rows * 16.  One kind::tf32 MMA consumes K = 8 (two 16-byte chunks); consecutive K steps advance the descriptor's
+// start address by 2 * LBO.  A row group offset advances it by 128 bytes per 8 rows.
+#pragma once
+#include <cstdint>
+#include "tma_common.cuh"
+
+namespace tnmf {
+namespace tc {
+
+using tma::mbar_arrive;
+using tma::mbar_fence_init;
+using tma::mbar_init;
+using tma::mbar_wait;
+using tma::smem_u32;
+
+__device__ __forceinline__ size_t canon_offset_floats(int i, int k, int rows) {
+    return (size_t)(i >> 3) * 32 + (size_t)(k >> 2) * ((size_t)rows * 4) + (size_t)(i & 7) * 4 + (size_t)(k & 3);
+}
+
+// 64-bit shared-memory matrix descriptor: start address, LBO, SBO (all >> 4), descriptor version 1 (Blackwell),
+// base offset 0, layout type 0 (no swizzle).
+__device__ __forceinline__ unsigned long long smem_desc(unsigned addr_bytes, unsigned lbo_bytes, unsigned sbo_bytes) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((addr_bytes >> 4) & 0x3FFFu);
+    d |= (unsigned long long)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (unsigned long long)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+
+// 32-bit instruction descriptor of kind::tf32: D = F32, A = B = TF32, both K-major, dense, M x N.
+__host__ __device__ constexpr unsigned idesc_tf32(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread.
+__device__ __forceinline__ void mma_tf32(unsigned tmem_d, unsigned long long desc_a, unsigned long long desc_b,
+                                         unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// mbarrier arrive once all tcgen05 operations issued so far by this thread have completed (implies
+// tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void mma_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (the tensor core reads operands through it)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// Whole-warp TMEM allocation of `cols` columns (power of two >= 32); the base address lands in *slot (shared).
+__device__ __forceinline__ void tmem_alloc(unsigned *slot, unsigned cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned base, unsigned cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(base), "r"(cols) : "memory");
+}
+
+// 16 consecutive columns of this thread's TMEM lane (lane = 32 * (warp % 4) + laneid) -> 16 registers.
+__device__ __forceinline__ void tmem_ld16(unsigned addr, float (&v)[16]) {
+    unsigned r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(addr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// x = hi + lo with hi the nearest TF32 (10-bit mantissa) and lo the remainder (the MMA truncates it to TF32).
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+    unsigned h;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+}  // namespace tc
+}  // namespace tnmf
