@@ -95,7 +95,7 @@ def build(force: bool = False, verbose: bool = False, jobs: Optional[int] = None
             src, obj, defs = pending.pop(0)
             obj = os.path.join(objdir, obj)
             objs.append(obj)
-            cmd = [nvcc, *NVCC_FLAGS, *defs, '-Xptxas', '-v', '-c', os.path.join(CSRC, src), '-o', obj]
+            cmd = [nvcc, *NVCC_FLAGS, *os.environ.get('TNMF_NVCC_EXTRA', '').split(), *defs, '-Xptxas', '-v', '-c', os.path.join(CSRC, src), '-o', obj]
             running.append((f'{src} {" ".join(defs)}',
                             subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         name, pr = running.pop(0)

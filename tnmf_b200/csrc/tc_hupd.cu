@@ -5,8 +5,10 @@
 //   epilogue (H given):  pos += lambda*(G-H); pos += lambda_c*(Gsum-G); pos += reg; H = (H*neg)/pos
 //                                                           (tnmf/TransformInvariantNMF.py:217-235,246-271)
 //
-// Formulation.  A CTA owns a tile of 128 activation COLUMNS - column q = (sample n, position tx), the flattened
-// [N x TX] space cut into runs of 128, so partial rows never waste MMA lanes - and walks down the rows.  For a source
+// Formulation.  A CTA owns a tile of 128 activation COLUMNS and walks down the rows.  Column J = n * TXP + xv lives
+// in the flattened [N x TXP] space, TXP = TX + AX - 1: the AX-1 gap columns behind every sample (computed, never
+// stored) make the source windows of different samples disjoint, so a tile may span samples and partial rows cost a
+// few percent of the MMA lanes instead of a whole padded tile.  For a source
 // row r of X (V or R) the "expander" warps build, once,
 //       A_r[column i, k = (c, ax)] = Xext[n_i, c, r, tx_i - offx + ax]          128 x KP,  KP = roundup(C*AX, 8)
 // in shared memory (canonical K-major no-swizzle layout, hi/lo TF32 split).  Source row r contributes to the output
@@ -18,11 +20,27 @@
 // FP32 accumulation in TMEM.  When the last source row of an output row has been issued, a tcgen05.commit hands the
 // slot to the epilogue warps, which read it back (tcgen05.ld), apply the update and release the slot.
 //
-// Roles (288 threads): warps 0-3 expanders (thread = column), warps 4-7 epilogue (thread = column = TMEM lane),
-// warp 8 = one elected thread issuing the MMAs.  mbarriers: a_full/a_empty per operand stage, row_done/slot_free per
+// Expansion: the source row segment of the tile (C x (128 + AX - 1) values, zero outside the sample) is fetched one
+// stage ahead into registers, split into hi/lo once per element and parked in a small double-buffered "raw" array;
+// every expander thread then copies its C*AX-wide window into the operand stage with LDS.32 / STS.128 only.
+//
+// Roles (448 threads): warps 0-7 expanders (thread = column x half of the K groups), warps 8-11 epilogue (thread =
+// column = TMEM lane), warps 12 and 13 issue the MMAs of the V stages (neg accumulators) and of the R stages (pos) - converged warps, one
+// elected lane issuing, because a single issuing thread cannot feed the tensor pipe at N <= 176.  mbarriers: a_full/a_empty per operand stage, row_done/slot_free per
 // TMEM slot.  Atoms are processed in blocks of 16 (one launch per block).
 // Bound: tensor pipe at the TF32 rate / 3.
+#include <cstdlib>
 #include "tc_common.cuh"
+
+// -DTNMF_TC_PROFILE: CTA 0 prints, per role, the cycles it spent blocked on each of its barriers (debug builds only)
+#ifdef TNMF_TC_PROFILE
+#include <cstdio>
+#define TC_PROF_DECL(n) long long prof_##n = 0
+#define TC_PROF_WAIT(n, stmt) do { const long long t__ = clock64(); stmt; prof_##n += clock64() - t__; } while (0)
+#else
+#define TC_PROF_DECL(n)
+#define TC_PROF_WAIT(n, stmt) stmt
+#endif
 
 namespace tnmf {
 namespace tc {
@@ -35,11 +53,14 @@ constexpr int kTile = 128;          // activation columns per CTA tile = MMA M
 constexpr int kNB = 16;             // atoms per launch = MMA N granule
 constexpr int kSlots = 16;          // TMEM ring: 16 output rows x (16 neg + 16 pos columns)
 constexpr int kMaxStages = 6;
-constexpr int kThreads = 32 * 9;
+constexpr int kExpanders = 256;       // 8 expander warps: thread = (column, half of the K groups)
+constexpr int kThreads = 32 * 14;     // 8 expander + 4 epilogue + 2 MMA-issuing warps
 constexpr int kMaxSmem = 226 * 1024;
+constexpr int kRawMax = 4;          // raw-row elements per expander thread (C * (128 + AX - 1) <= 1024)
 
 struct TcHupdPlan {
     int KP, ksteps;                 // padded contraction length C*AX -> multiple of 8
+    int TXP, RW, raw_floats, nraw;  // padded columns per sample, raw row width, floats per raw array, raw loads/thread
     int tiles, rblocks, rows_per_block;
     long long units;
     int n_stages, stage_floats, w_floats;
@@ -59,15 +80,22 @@ bool make_tc_hupd_plan(const Geo2 &g, TcHupdPlan &p) {
     p = TcHupdPlan();
     if (g.AY > kSlots - 1 || g.AY < 1) return false;
     p.KP = round_up(g.C * g.AX, 8);
+    if (p.KP > 64) return false;                            // KGT <= 16
     p.ksteps = p.KP / 8;
     p.stage_floats = 2 * kTile * p.KP;                     // hi + lo
     p.w_floats = 2 * g.AY * kNB * p.KP;                    // hi + lo, atom-row blocks in ring order
-    const size_t fixed = (size_t)p.w_floats * 4 + 1024;
+    p.TXP = g.TX + g.AX - 1;
+    p.RW = kTile + g.AX - 1;
+    p.raw_floats = round_up(g.C * p.RW + kTile, 32);        // + 128 zeros read by the padded k
+    p.nraw = ceil_div(g.C * p.RW, kExpanders);
+    if (p.nraw > kRawMax) return false;
+    const size_t fixed = (size_t)p.w_floats * 4 + (size_t)4 * p.raw_floats * 4 + 1024;
     if (fixed + 2 * (size_t)p.stage_floats * 4 > (size_t)kMaxSmem) return false;
     p.n_stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)p.stage_floats * 4));
     if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
+    p.n_stages &= ~1;                                       // V stages even, R stages odd: one issuing warp each
     p.smem = fixed + (size_t)p.n_stages * p.stage_floats * 4;
-    const long long cols = (long long)g.N * g.TX;
+    const long long cols = (long long)g.N * p.TXP;
     if (cols <= 0 || cols >= (1ll << 31) - kTile) return false;
     p.tiles = (int)((cols + kTile - 1) / kTile);
     // row blocks: minimise waves * (rows + per-unit overhead)
@@ -100,6 +128,8 @@ __device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const TcHu
     return w;
 }
 
+// KGH: compile-time bound on the 16-byte K groups one expander thread copies (ceil(KP / 8) <= KGH)
+template <int KGH>
 __global__ void __launch_bounds__(kThreads, 1)
 hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
     extern __shared__ __align__(128) float smem[];
@@ -110,14 +140,19 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
     const int KP = p.KP, AY = g.AY, AX = g.AX, C = g.C;
     const int NR = AY * kNB;                               // rows of the atom operand
     float *w_hi = smem, *w_lo = smem + NR * KP;
-    float *stages = smem + p.w_floats;
+    float *raw = smem + p.w_floats;                         // [2 buffers][hi, lo][raw_floats]
+    float *stages = raw + 4 * p.raw_floats;
+    __shared__ __align__(16) int koff[64];                                // k -> offset of (c, ax) in a raw array (padding -> zeros)
+    const int RW = p.RW;
+    if (tid < KP) koff[tid] = tid < C * AX ? (tid / AX) * RW + (tid % AX) : C * RW;
+    for (int idx = tid; idx < 4 * kTile; idx += kThreads) raw[(idx / kTile) * p.raw_floats + C * RW + (idx % kTile)] = 0.f;
 
     if (tid == 0) {
-        for (int s = 0; s < p.n_stages; ++s) { mbar_init(&a_full[s], kTile); mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < kSlots; ++s) { mbar_init(&row_done[s], 1); mbar_init(&slot_free[s], kTile); }
+        for (int s = 0; s < p.n_stages; ++s) { mbar_init(&a_full[s], kExpanders); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < kSlots; ++s) { mbar_init(&row_done[s], 2); mbar_init(&slot_free[s], kTile); }
         mbar_fence_init();
     }
-    if (warp == 8) tmem_alloc(&tmem_base_s, 512);
+    if (warp == 12) tmem_alloc(&tmem_base_s, 512);
     // atom operand: row n = j*16 + ml  <->  atom m0+ml, atom row ay = AY-1-j;  k = c*AX + ax
     for (int idx = tid; idx < NR * KP; idx += kThreads) {
         const int n = idx / KP, k = idx - n * KP;
@@ -139,88 +174,154 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
     __syncthreads();
     tc_fence_after();
     const unsigned tmem_base = tmem_base_s;
-    const long long total_cols = (long long)g.N * g.TX;
 
-    if (warp < 4) {
+    if (warp < 8) {
         // ------------------------------------ expanders ------------------------------------
-        const int i = tid;
+        const int i = tid & (kTile - 1), half = tid >> 7;
         int st = 0;
-        unsigned ph = 0;
+        unsigned ph = 0, buf = 0;
+        TC_PROF_DECL(empty); TC_PROF_DECL(bar); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         const long long plane = (long long)g.DY * g.DX;
         const int KG = KP >> 2;
+        const int kg0 = half * ((KG + 1) >> 1), kg1 = half ? KG : ((KG + 1) >> 1);   // this thread's K groups
+        const int raw_count = C * RW;
+        int4 ko[KGH];                           // raw-array offsets of the 4 k of every K group (same for all stages)
+#pragma unroll
+        for (int j = 0; j < KGH; ++j)
+            ko[j] = kg0 + j < kg1 ? *reinterpret_cast<const int4 *>(&koff[4 * (kg0 + j)]) : make_int4(0, 0, 0, 0);
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
-            const long long q = (long long)w.tile * kTile + i;
-            const bool active = q < total_cols;
-            const int n = active ? (int)(q / g.TX) : 0;
-            const int xs = (active ? (int)(q - (long long)n * g.TX) : 0) - g.offx;
-            for (int r = w.r_lo; r <= w.r_hi; ++r) {
-                for (int x = 0; x < 2; ++x) {
-                    const float *src = (x ? a.R : a.V) + (long long)n * C * plane + (long long)r * g.DX;
-                    mbar_wait(&a_empty[st], ph ^ 1u);
-                    float *d_hi = stages + (size_t)st * p.stage_floats + (size_t)(i >> 3) * 32 + (size_t)(i & 7) * 4;
-                    float *d_lo = d_hi + kTile * KP;
-                    int c = 0, ax = 0;
-                    for (int kg0 = 0; kg0 < KG; kg0 += 4) {
-                        float v[16];
+            // source element of every raw slot (q = tid + 256 e -> channel q / RW, position q % RW) in row 0, or -1: zero
+            long long roff[kRawMax];
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            const int xx = xs + ax;
-                            const bool ok = active && c < C && (unsigned)xx < (unsigned)g.DX && (kg0 * 4 + e) < KP;
-                            v[e] = ok ? __ldg(src + (long long)c * plane + xx) : 0.f;
-                            if (++ax == AX) { ax = 0; ++c; }
-                        }
-#pragma unroll
-                        for (int gq = 0; gq < 4; ++gq) {
-                            if (kg0 + gq < KG) {
-                                float4 hi, lo;
-                                split_tf32(v[4 * gq + 0], hi.x, lo.x);
-                                split_tf32(v[4 * gq + 1], hi.y, lo.y);
-                                split_tf32(v[4 * gq + 2], hi.z, lo.z);
-                                split_tf32(v[4 * gq + 3], hi.w, lo.w);
-                                *reinterpret_cast<float4 *>(d_hi + (size_t)(kg0 + gq) * (kTile * 4)) = hi;
-                                *reinterpret_cast<float4 *>(d_lo + (size_t)(kg0 + gq) * (kTile * 4)) = lo;
-                            }
-                        }
-                    }
-                    fence_proxy_async();
-                    mbar_arrive(&a_full[st]);
-                    if (++st == p.n_stages) { st = 0; ph ^= 1u; }
+            for (int e = 0; e < kRawMax; ++e) {
+                roff[e] = -1;
+                const int q = tid + kExpanders * e;
+                if (e < p.nraw && q < raw_count) {
+                    const int c = q / RW;
+                    const long long J = (long long)w.tile * kTile + (q - c * RW);
+                    const int n = (int)(J / p.TXP);
+                    const int x = (int)(J - (long long)n * p.TXP) - g.offx;
+                    if (n < g.N && (unsigned)x < (unsigned)g.DX) roff[e] = ((long long)n * C + c) * plane + x;
                 }
             }
+            float rv[kRawMax];
+            auto load_raw = [&](int sidx) {
+                const float *src = ((sidx & 1) ? a.R : a.V) + (long long)(w.r_lo + (sidx >> 1)) * g.DX;
+#pragma unroll
+                for (int e = 0; e < kRawMax; ++e) rv[e] = roff[e] >= 0 ? __ldg(src + roff[e]) : 0.f;
+            };
+            const int n_st = 2 * (w.r_hi - w.r_lo + 1);
+            load_raw(0);
+            for (int sidx = 0; sidx < n_st; ++sidx) {
+                float *raw_hi = raw + (size_t)buf * 2 * p.raw_floats, *raw_lo = raw_hi + p.raw_floats;
+#pragma unroll
+                for (int e = 0; e < kRawMax; ++e) {
+                    if (e < p.nraw && tid + kExpanders * e < raw_count) {
+                        float hi, lo;
+                        split_tf32(rv[e], hi, lo);
+                        raw_hi[tid + kExpanders * e] = hi;
+                        raw_lo[tid + kExpanders * e] = lo;
+                    }
+                }
+                if (sidx + 1 < n_st) load_raw(sidx + 1);             // in flight while this stage is expanded
+                TC_PROF_WAIT(bar, asm volatile("bar.sync 1, 256;\n" ::: "memory"));
+                TC_PROF_WAIT(empty, mbar_wait(&a_empty[st], ph ^ 1u));
+                float *d_hi = stages + (size_t)st * p.stage_floats + (size_t)(i >> 3) * 32 + (size_t)(i & 7) * 4 +
+                              (size_t)kg0 * (kTile * 4);
+                float *d_lo = d_hi + kTile * KP;
+                const float *s_hi = raw_hi + i, *s_lo = raw_lo + i;
+                // two K groups per batch: 16 independent LDS in flight before the 4 STS.128
+#pragma unroll
+                for (int j = 0; j < KGH; j += 2) {
+                    if (kg0 + j < kg1) {
+                        const int4 o0 = ko[j];
+                        const float4 h0 = make_float4(s_hi[o0.x], s_hi[o0.y], s_hi[o0.z], s_hi[o0.w]);
+                        const float4 l0 = make_float4(s_lo[o0.x], s_lo[o0.y], s_lo[o0.z], s_lo[o0.w]);
+                        if (j + 1 < KGH && kg0 + j + 1 < kg1) {
+                            const int4 o1 = ko[j + 1 < KGH ? j + 1 : j];
+                            const float4 h1 = make_float4(s_hi[o1.x], s_hi[o1.y], s_hi[o1.z], s_hi[o1.w]);
+                            const float4 l1 = make_float4(s_lo[o1.x], s_lo[o1.y], s_lo[o1.z], s_lo[o1.w]);
+                            *reinterpret_cast<float4 *>(d_hi + (size_t)(j + 1) * (kTile * 4)) = h1;
+                            *reinterpret_cast<float4 *>(d_lo + (size_t)(j + 1) * (kTile * 4)) = l1;
+                        }
+                        *reinterpret_cast<float4 *>(d_hi + (size_t)j * (kTile * 4)) = h0;
+                        *reinterpret_cast<float4 *>(d_lo + (size_t)j * (kTile * 4)) = l0;
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[st]);
+                if (++st == p.n_stages) { st = 0; ph ^= 1u; }
+                buf ^= 1u;
+            }
         }
-    } else if (warp < 8) {
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && tid == 0)
+            printf("expander: total %lld  wait a_empty %lld  raw barrier %lld\n", prof_total, prof_empty, prof_bar);
+#endif
+    } else if (warp < 12) {
         // ------------------------------------ epilogue ------------------------------------
-        const int i = tid - kTile;
+        const int i = tid - kExpanders;
         const unsigned lane_base = (unsigned)((warp & 3) * 32) << 16;
         const long long tvol = (long long)g.TY * g.TX;
         long long g_base = 0;
+        TC_PROF_DECL(done); TC_PROF_DECL(total); TC_PROF_DECL(ldtm); TC_PROF_DECL(arrive);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
-            const long long q = (long long)w.tile * kTile + i;
-            const bool active = q < total_cols;
-            const int n = active ? (int)(q / g.TX) : 0;
-            const int tx = active ? (int)(q - (long long)n * g.TX) : 0;
+            const long long J = (long long)w.tile * kTile + i;
+            const int n = (int)(J / p.TXP);
+            const int tx = (int)(J - (long long)n * p.TXP);
+            const bool active = n < g.N && tx < g.TX;
+            // the activations of a row do not depend on the accumulators: they are fetched one row ahead
+            float hnext[kNB];
+            float *hrow = (a.H && active) ? a.H + (long long)n * g.hsn + (long long)a.m0 * g.hsm + tx : nullptr;
+            auto load_h = [&](int ty) {
+#pragma unroll
+                for (int ml = 0; ml < kNB; ++ml)
+                    hnext[ml] = (hrow && a.m0 + ml < g.M) ? hrow[(long long)ty * g.hsy + (long long)ml * g.hsm] : 0.f;
+            };
+            const bool fast = a.H && !a.G && a.m0 + kNB <= g.M;
+            load_h(w.ty0);
             for (int ty = w.ty0; ty < w.ty1; ++ty) {
                 const long long gi = g_base + (ty - w.ty0);
                 const int s = (int)(gi & (kSlots - 1));
                 const unsigned par = (unsigned)((gi >> 4) & 1);
-                // the activations of this row do not depend on the accumulators: fetch them while the MMAs run
-                float hv[kNB];
-                float *hp = a.H ? a.H + (long long)n * g.hsn + (long long)ty * g.hsy + tx : nullptr;
-                if (a.H) {
-#pragma unroll
-                    for (int ml = 0; ml < kNB; ++ml)
-                        hv[ml] = (active && a.m0 + ml < g.M) ? hp[(long long)(a.m0 + ml) * g.hsm] : 0.f;
-                }
-                mbar_wait(&row_done[s], par);
+                TC_PROF_WAIT(done, mbar_wait(&row_done[s], par));
                 tc_fence_after();
                 float neg[kNB], pos[kNB];
-                tmem_ld16(tmem_base + lane_base + (unsigned)(s * kNB), neg);
-                tmem_ld16(tmem_base + lane_base + 256u + (unsigned)(s * kNB), pos);
-                tmem_ld_wait();
+                TC_PROF_WAIT(ldtm, tmem_ld16(tmem_base + lane_base + (unsigned)(s * kNB), neg);
+                             tmem_ld16(tmem_base + lane_base + 256u + (unsigned)(s * kNB), pos); tmem_ld_wait());
                 tc_fence_before();
-                mbar_arrive(&slot_free[s]);
+                TC_PROF_WAIT(arrive, mbar_arrive(&slot_free[s]));
+                float hv[kNB];
+#pragma unroll
+                for (int ml = 0; ml < kNB; ++ml) hv[ml] = hnext[ml];
+                if (fast) {
+                    // plain fused update of a full block of 16 atoms: pointer walks, no per-atom tests.  The quotient
+                    // uses the reciprocal unit (2 ulp): its error is below that of the 3xTF32 products it divides.
+                    if (active) {
+                        float *o = hrow + (long long)ty * g.hsy;
+                        if (ty + 1 < w.ty1) {
+                            const float *q = o + g.hsy;
+#pragma unroll
+                            for (int ml = 0; ml < kNB; ++ml) { hnext[ml] = *q; q += g.hsm; }
+                        }
+#pragma unroll
+                        for (int ml = 0; ml < kNB; ++ml) {
+                            *o = __fdividef(hv[ml] * neg[ml], pos[ml] + a.reg);
+                            o += g.hsm;
+                        }
+                    }
+                    continue;
+                }
+                if (ty + 1 < w.ty1) load_h(ty + 1);
                 if (!active) continue;
                 const long long tin = (long long)ty * g.TX + tx;
 #pragma unroll
@@ -242,7 +343,7 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
                         ps += a.reg;
                         float hn = h * neg[ml];
                         hn /= ps;
-                        hp[(long long)m * g.hsm] = hn;
+                        hrow[(long long)ty * g.hsy + (long long)ml * g.hsm] = hn;
                     } else {
                         a.neg[cidx] = neg[ml];
                         a.pos[cidx] = pos[ml];
@@ -251,15 +352,29 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
             }
             g_base += w.ty1 - w.ty0;
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && i == 0) printf("epilogue: total %lld  wait row_done %lld  ldtm %lld  arrive %lld\n", prof_total, prof_done, prof_ldtm, prof_arrive);
+#endif
     } else {
-      if (lane == 0) {
+      {
         // ------------------------------------ MMA issuer ------------------------------------
+        // the whole warp walks the schedule (converged, uniform registers); one elected lane issues
+        // descriptors: only the 14-bit start-address field changes between MMAs, so they are kept as (lo, hi) words
         const unsigned lbo_a = kTile * 16, lbo_b = (unsigned)NR * 16;
-        const unsigned w_hi_addr = smem_u32(w_hi), w_lo_addr = smem_u32(w_lo);
+        const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
+        const unsigned a_lo_word = ((lbo_a >> 4) << 16), b_lo_word = ((lbo_b >> 4) << 16);
+        const unsigned w_addr16[3] = {smem_u32(w_hi) >> 4, smem_u32(w_hi) >> 4, smem_u32(w_lo) >> 4};
         const unsigned stage_addr0 = smem_u32(stages);
-        int st = 0;
+        const unsigned a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
+        const int x = warp - 12;                // warp 12 issues the V stages (neg accumulators), warp 13 the R stages (pos)
+        int st = x;
         unsigned ph = 0;
         long long g_base = 0;
+        TC_PROF_DECL(full); TC_PROF_DECL(slot); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             int next_new = w.ty0, next_done = w.ty0;
@@ -271,58 +386,94 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
                 const int first_new = next_new;
                 for (; next_new <= t_b; ++next_new) {
                     const long long gi = g_base + (next_new - w.ty0);
-                    if (gi >= kSlots) mbar_wait(&slot_free[gi & (kSlots - 1)], (unsigned)(((gi >> 4) - 1) & 1));
+                    if (gi >= kSlots)
+                        TC_PROF_WAIT(slot, mbar_wait(&slot_free[gi & (kSlots - 1)], (unsigned)(((gi >> 4) - 1) & 1)));
                 }
                 tc_fence_after();
-                for (int x = 0; x < 2; ++x) {
-                    mbar_wait(&a_full[st], ph);
+                // the MMAs of this source row: up to two column runs of the ring for the rows that accumulate ...
+                unsigned o_col[2], o_idesc[2], o_b16[2];
+                int n_ops = 0;
+                auto add_ops = [&](int lo, int hi, unsigned *col, unsigned *idesc, unsigned *b16, int &n) {
+                    if (lo > hi) return;
+                    const int cnt = hi - lo + 1;
+                    const int s = (int)((g_base + (lo - w.ty0)) & (kSlots - 1));
+                    const int first = min(cnt, kSlots - s);
+                    col[n] = (unsigned)(s * kNB); idesc[n] = idesc_tf32(kTile, kNB * first);
+                    b16[n] = (unsigned)(lo - j0) * 16u; ++n;
+                    if (cnt > first) {
+                        col[n] = 0u; idesc[n] = idesc_tf32(kTile, kNB * (cnt - first));
+                        b16[n] = (unsigned)(lo - j0 + first) * 16u; ++n;
+                    }
+                };
+                add_ops(t_a, t_b, o_col, o_idesc, o_b16, n_ops);
+                // ... and, for the very first MMA of the row, the same split into old rows (accumulate) / new rows (overwrite)
+                unsigned f_col[4], f_idesc[4], f_b16[4];
+                int n_old = 0, n_first = 0;
+                if (first_new <= t_b) {
+                    add_ops(t_a, first_new - 1, f_col, f_idesc, f_b16, n_first);
+                    n_old = n_first;
+                    add_ops(max(first_new, t_a), t_b, f_col, f_idesc, f_b16, n_first);
+                }
+                {
+                    TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
                     tc_fence_after();
                     const unsigned col_base = tmem_base + (x ? 256u : 0u);
-                    const unsigned a_hi_addr = stage_addr0 + (unsigned)st * (unsigned)p.stage_floats * 4u;
-                    const unsigned a_lo_addr = a_hi_addr + kTile * KP * 4u;
+                    const unsigned a_hi16 = (stage_addr0 + (unsigned)st * (unsigned)p.stage_floats * 4u) >> 4;
+                    const unsigned a_addr16[3] = {a_hi16, a_hi16 + ((kTile * KP * 4u) >> 4), a_hi16};
                     for (int ks = 0; ks < p.ksteps; ++ks) {
 #pragma unroll
                         for (int t = 0; t < 3; ++t) {
                             const unsigned long long da =
-                                smem_desc((t == 1 ? a_lo_addr : a_hi_addr) + ks * 2 * lbo_a, lbo_a, 128);
-                            const unsigned b_addr = (t == 2 ? w_lo_addr : w_hi_addr) + ks * 2 * lbo_b;
-                            // rows [lo, hi] of the window, accumulate flag
-                            auto issue = [&](int lo, int hi, unsigned acc) {
-                                if (lo > hi) return;
-                                const int cnt = hi - lo + 1;
-                                const int s = (int)((g_base + (lo - w.ty0)) & (kSlots - 1));
-                                const int first = min(cnt, kSlots - s);
-                                mma_tf32(col_base + (unsigned)(s * kNB), da,
-                                         smem_desc(b_addr + (unsigned)(lo - j0) * 256u, lbo_b, 128),
-                                         idesc_tf32(kTile, kNB * first), acc);
-                                if (cnt > first)
-                                    mma_tf32(col_base, da,
-                                             smem_desc(b_addr + (unsigned)(lo - j0 + first) * 256u, lbo_b, 128),
-                                             idesc_tf32(kTile, kNB * (cnt - first)), acc);
-                            };
-                            if (ks == 0 && t == 0 && first_new <= t_b) {
-                                issue(t_a, first_new - 1, 1u);
-                                issue(max(first_new, t_a), t_b, 0u);
+                                ((unsigned long long)desc_hi << 32) | (a_lo_word | (a_addr16[t] + ks * a_step16));
+                            const unsigned b16 = w_addr16[t] + ks * b_step16;
+                            if (ks == 0 && t == 0 && n_first > 0) {
+#pragma unroll
+                                for (int o = 0; o < 4; ++o)
+                                    if (o < n_first)
+                                        mma_tf32_elect(col_base + f_col[o], da,
+                                                 ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + f_b16[o])),
+                                                 f_idesc[o], o < n_old ? 1u : 0u);
                             } else {
-                                issue(t_a, t_b, 1u);
+                                mma_tf32_elect(col_base + o_col[0], da,
+                                         ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[0])), o_idesc[0], 1u);
+                                if (n_ops > 1)
+                                    mma_tf32_elect(col_base + o_col[1], da,
+                                             ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[1])),
+                                             o_idesc[1], 1u);
                             }
                         }
                     }
-                    mma_commit(&a_empty[st]);
-                    if (++st == p.n_stages) { st = 0; ph ^= 1u; }
+                    mma_commit_elect(&a_empty[st]);
+                    st += 2;
+                    if (st >= p.n_stages) { st = x; ph ^= 1u; }
                 }
-                // output rows whose last source row this was
+                // output rows whose last source row this was (the barrier needs the commit of both issuing warps)
                 for (; next_done < w.ty1 && min(g.DY - 1, next_done - g.offy + AY - 1) <= r; ++next_done)
-                    mma_commit(&row_done[(g_base + (next_done - w.ty0)) & (kSlots - 1)]);
+                    mma_commit_elect(&row_done[(g_base + (next_done - w.ty0)) & (kSlots - 1)]);
             }
             g_base += w.ty1 - w.ty0;
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && lane == 0 && x == 0)
+            printf("mma: total %lld  wait a_full %lld  wait slot_free %lld\n", prof_total, prof_full, prof_slot);
+#endif
       }
       __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem_base, 512);
+    if (warp == 12) tmem_dealloc(tmem_base, 512);
+}
+
+template <int KGH>
+static int launch(const Geo2 &g, const TcHupdPlan &p, const TcHupdArgs &a, cudaStream_t st) {
+    auto kern = hupd_tc_kernel<KGH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    kern<<<(unsigned)p.grid, kThreads, p.smem, st>>>(g, p, a);
+    TNMF_CHECK_LAUNCH();
+    return TNMF_OK;
 }
 
 }  // namespace tc
@@ -342,16 +493,23 @@ int tc_gradient_h(const Geo &g, const float *V, const float *R, const float *W, 
     const tiled::Geo2 q = tiled::make_geo2(g);
     tc::TcHupdPlan p;
     if (!tc::make_tc_hupd_plan(q, p)) return TNMF_EUNSUPPORTED;
-    cudaError_t e = cudaFuncSetAttribute(tc::hupd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMaxSmem);
-    if (e != cudaSuccess) return status_from_cuda(e);
     tc::TcHupdArgs a;
     a.V = V; a.R = R; a.W = W; a.neg = neg; a.pos = pos; a.H = H;
     a.reg = (float)reg; a.lambda = (float)lambda; a.lambda_cross = (float)lambda_cross;
     a.G = G; a.Gsum = Gsum;
     for (int m0 = 0; m0 < g.M; m0 += tc::kNB) {
         a.m0 = m0;
-        tc::hupd_tc_kernel<<<(unsigned)p.grid, tc::kThreads, p.smem, st>>>(q, p, a);
-        TNMF_CHECK_LAUNCH();
+        int s;
+        const int kgh = (p.KP / 4 + 1) / 2;                 // K groups per expander thread
+        if (kgh <= 1) s = tc::launch<1>(q, p, a, st);
+        else if (kgh <= 2) s = tc::launch<2>(q, p, a, st);
+        else if (kgh <= 3) s = tc::launch<3>(q, p, a, st);
+        else if (kgh <= 4) s = tc::launch<4>(q, p, a, st);
+        else if (kgh <= 5) s = tc::launch<5>(q, p, a, st);
+        else if (kgh <= 6) s = tc::launch<6>(q, p, a, st);
+        else if (kgh <= 8) s = tc::launch<8>(q, p, a, st);
+        else s = TNMF_EUNSUPPORTED;
+        if (s) return s;
     }
     return TNMF_OK;
 }

@@ -96,7 +96,75 @@ static double run(int KP, int NR, int jb, int N, int col0, int terms, int passes
     return worst;
 }
 
+// Timing: `count` MMAs of shape 128 x N x 8 issued back to back by one thread, accumulating into `ndst` alternating
+// TMEM column ranges; cycles from first issue to the commit's arrival.
+__global__ void __launch_bounds__(128, 1) time_kernel(long long *out, int N, int count, int ndst, int KP, int NR) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ unsigned tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int idx = tid; idx < (128 + NR) * KP; idx += 128) smem[idx] = 1.0f;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = tmem_base_s;
+    if (tid == 0) {
+        const unsigned lbo_a = 128 * 16, lbo_b = (unsigned)NR * 16;
+        const unsigned idesc = idesc_tf32(128, N);
+        const unsigned a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * KP);
+        const int ks_n = KP / 8;
+        long long t0 = clock64();
+        (void)ks_n;
+        const unsigned long long da0 = smem_desc(a0, lbo_a, 128), db0 = smem_desc(b0, lbo_b, 128);
+        const unsigned long long da1 = smem_desc(a0 + 2 * lbo_a, lbo_a, 128), db1 = smem_desc(b0 + 2 * lbo_b, lbo_b, 128);
+        const unsigned d0 = tmem_base, d1 = tmem_base + (ndst > 1 ? 256u : 0u);
+        mma_tf32(d0, da0, db0, idesc, 0u);
+        mma_tf32(d1, da0, db0, idesc, 0u);
+        for (int i = 0; i < count; i += 4) {
+            mma_tf32(d0, da0, db0, idesc, 1u);
+            mma_tf32(d1, da1, db1, idesc, 1u);
+            mma_tf32(d0, da1, db1, idesc, 1u);
+            mma_tf32(d1, da0, db0, idesc, 1u);
+        }
+        long long t1 = clock64();
+        mma_commit(&bar);
+        mbar_wait(&bar, 0);
+        long long t2 = clock64();
+        out[0] = t1 - t0;
+        out[1] = t2 - t0;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+static void time_it(int N, int count, int ndst) {
+    const int KP = 40, NR = 256;
+    long long *d, h[2];
+    cudaMalloc(&d, 16);
+    const size_t smem = (size_t)(128 + NR) * KP * 4;
+    cudaFuncSetAttribute(time_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int rep = 0; rep < 2; ++rep) {
+        time_kernel<<<1, 128, smem>>>(d, N, count, ndst, KP, NR);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(1); }
+    }
+    cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+    printf("N=%3d count=%4d ndst=%d : issue %6lld clk (%.1f/mma)  complete %7lld clk (%.1f/mma, ideal %.1f)\n", N, count, ndst,
+           h[0], (double)h[0] / count, h[1], (double)h[1] / count, N / 2.0);
+    cudaFree(d);
+}
+
 int main() {
+    for (int N : {16, 32, 64, 96, 128, 176, 240, 256}) time_it(N, 400, 1);
+    time_it(176, 400, 2);
+    time_it(64, 400, 2);
+    time_it(64, 400, 4);
+    time_it(16, 400, 8);
+
     printf("1xTF32  KP=8   NR=16  N=16        : max rel err %.3e\n", run(8, 16, 0, 16, 0, 1, 1));
     printf("3xTF32  KP=8   NR=16  N=16        : max rel err %.3e\n", run(8, 16, 0, 16, 0, 3, 1));
     printf("3xTF32  KP=40  NR=176 N=176 col 48: max rel err %.3e\n", run(40, 176, 0, 176, 48, 3, 1));
