@@ -215,13 +215,13 @@ def run_b200(args, w):
     torch.manual_seed(99)       # same W on every rank (it is broadcast anyway)
 
     nmf = TransformInvariantNMF(n_atoms=w['M'], atom_shape=w['A'], backend='b200', init='device',
-                                input_is_local_shard=True, kernel_path=args.kernel_path)
+                                input_is_local_shard=True, kernel_path=args.kernel_path,
+                                cuda_graph=not args.no_cuda_graph)
     be = nmf._backend                                                    # pylint: disable=protected-access
     nmf._initialize_matrices(V, keep_W=False)                            # pylint: disable=protected-access
 
-    def step():
-        nmf._update_H()                                                  # pylint: disable=protected-access
-        nmf._update_W()                                                  # pylint: disable=protected-access
+    # one batch MU iteration exactly as fit_batch runs it: eager the first time, CUDA-graph replays afterwards
+    step = nmf._batch_step()                                             # pylint: disable=protected-access
 
     for _ in range(args.warmup):
         step()
@@ -233,7 +233,6 @@ def run_b200(args, w):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    be.kernel_events = {}
     launches0 = be.launches
     t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,8 +246,14 @@ def run_b200(args, w):
     torch.cuda.synchronize(device)
     t_wall1 = time.perf_counter()
     launches = be.launches - launches0
-    events, be.kernel_events = be.kernel_events, None
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    # per-kernel durations: the same iteration launched eagerly with a CUDA-event pair around every hot-path call
+    be.kernel_events = {}
+    n_probe = min(args.steps, 5)
+    for _ in range(n_probe):
+        step()
+    torch.cuda.synchronize(device)
+    events, be.kernel_events = be.kernel_events, None
 
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
     if world > 1:
@@ -258,7 +263,7 @@ def run_b200(args, w):
 
     # per-kernel averages over the timed region (CUDA events on the launching stream)
     kern_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) for k, v in events.items()}
-    kern_calls = {k: len(v) / args.steps for k, v in events.items()}
+    kern_calls = {k: len(v) / n_probe for k, v in events.items()}
     energy = float(nmf._energy_function())                               # pylint: disable=protected-access
     if not np.isfinite(energy):
         raise RuntimeError('non-finite energy after the timed iterations')
@@ -267,7 +272,8 @@ def run_b200(args, w):
     V_host = V.cpu().pin_memory()
     e2e_iters = args.steps
     nmf_e = TransformInvariantNMF(n_atoms=w['M'], atom_shape=w['A'], backend='b200', init='device',
-                                  input_is_local_shard=True, kernel_path=args.kernel_path)
+                                  input_is_local_shard=True, kernel_path=args.kernel_path,
+                                  cuda_graph=not args.no_cuda_graph)
     nmf_e.fit(V_host, n_iterations=1)                                    # warm-up (allocations)
     torch.cuda.synchronize(device)
     if world > 1:
@@ -353,7 +359,8 @@ def run_b200(args, w):
         'config': {'workload': f'{args.workload}: {w["text"]}', 'algorithm': 'batch MU (H update, W update)',
                    'samples_per_gpu': n_local, 'global_samples': world * n_local,
                    'parallelism': f'sample-sharded x{world}, all-reduce of the W gradient' if world > 1 else 'single GPU',
-                   'kernel_path': be.kernel_families(),
+                   'kernel_path': be.kernel_families(), 'launch': 'CUDA graph replay of one iteration' if nmf._cuda_graph  # pylint: disable=protected-access
+                   else 'eager launches',
                    'l2': 'working set (V, R, H) exceeds the 126 MB L2; no explicit flush'
                    if (bytes_step / 5 > 126e6) else 'working set fits L2; iterations overwrite H and R in between',
                    'final_energy': energy},
@@ -377,6 +384,7 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
     ap.add_argument('--kernel-path', default='auto', choices=['auto', 'generic', 'tiled', 'tma', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cuda-graph', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     w = WORKLOADS[args.workload]

@@ -68,19 +68,29 @@ def test_status_translation(lib):
     _lib.check(0)
 
 
-def test_tiled_path_selection(lib):
+def test_tiled_path_selection(lib, monkeypatch):
     f32_2d = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32)
     f64_2d = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F64)
     f32_3d = _lib.make_problem(2, 1, 2, (8, 8, 8), (3, 3, 3), _lib.TNMF_F32)
     assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_2d)) == 1
     assert lib.tnmf_uses_tiled_path(ctypes.byref(f64_2d)) == 0
     assert lib.tnmf_uses_tiled_path(ctypes.byref(f32_3d)) == 0
-    # operation by operation: TMA where the strides allow it (H rows of 266 floats are not 16-byte multiples)
+    # operation by operation: the tensor-core H update where most of every MMA is useful work, TMA where the strides
+    # allow it (H rows of 266 floats are not 16-byte multiples)
     fam = lambda p, op: lib.tnmf_kernel_family(ctypes.byref(p), op)
-    assert fam(f32_2d, _lib.OP_GRADIENT_H) == _lib.PATHS['tma']
+    assert fam(f32_2d, _lib.OP_GRADIENT_H) == _lib.PATHS['tc']
     assert fam(f32_2d, _lib.OP_RECONSTRUCT) == _lib.PATHS['tiled']
     padded = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, h_pitch=268)
+    assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma'], _lib.PATHS['tc'], _lib.PATHS['tma']]
+    monkeypatch.setenv('TNMF_NO_TC', '1')
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
+    monkeypatch.delenv('TNMF_NO_TC')
+    few_atoms = _lib.make_problem(8, 1, 3, (64, 64), (5, 5), _lib.TNMF_F32)       # 3 of 16 atoms, K 5 of 8: FP32 kernels
+    assert fam(few_atoms, _lib.OP_GRADIENT_H) == _lib.PATHS['tma']
+    tall_atom = _lib.make_problem(8, 2, 16, (64, 64), (16, 7), _lib.TNMF_F32)    # 16 atom rows do not fit the TMEM ring
+    assert fam(tall_atom, _lib.OP_GRADIENT_H) == _lib.PATHS['tma']
+    tall_atom.path = _lib.PATHS['tc']
+    assert fam(tall_atom, _lib.OP_GRADIENT_H) == _lib.PATHS['tma']               # 'tc' = tensor cores where a kernel exists
     circ = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, 'circular')
     assert [fam(circ, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
     one_d = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32)
