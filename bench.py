@@ -321,12 +321,30 @@ def run_b200(args, w):
             traffic, traffic_src = entry['bytes'], entry['source']
     except (OSError, ValueError):
         pass
+    families = be.kernel_families()
+    # tensor-pipe denominator of the 3xTF32 kernels: dense TF32 = half the measured dense bf16 rate, three MMAs per
+    # product -> useful flops at most bf16/6
+    bf16_peak, bf16_src = (peaks['bf16_tflops'], 'measured') if 'bf16_tflops' in peaks else (2250.0, 'nominal')
+    tc_peak = bf16_peak / 6.0
+    per_kernel = {}
+    for k in kernel_flops:
+        if k not in kern_ms:
+            continue
+        tf = kernel_flops[k] / (kern_ms[k] * 1e-3) / 1e12
+        on_tc = families.get(k) == 'tc'
+        pk = tc_peak if on_tc else fp32_peak
+        per_kernel[k] = {'family': families.get(k), 'bound': 'tensor (3xTF32)' if on_tc else 'fp32', 'ms': kern_ms[k],
+                         'launches_per_step': kern_calls[k], 'achieved_tflops': tf, 'peak_tflops': pk,
+                         'frac': (tf / pk) if pk else None}
+    dom = per_kernel[dominant]
     roofline = {
-        'bound': 'fp32', 'kernel': dominant, 'achieved': achieved, 'peak': fp32_peak, 'unit': 'TFLOP/s',
-        'frac': (achieved / fp32_peak) if fp32_peak else None, 'traffic': traffic, 'traffic_source': traffic_src,
-        'traffic_unit': 'bytes per launch (dram read + write, ncu)',
-        'peak_source': 'FP32-FMA probe kernel of libtnmf_b200.so timed in this run (MEASURED_PEAKS.json holds no '
-                       'FP32 figure); nominal 148 SM x 128 FMA x 2 x 1.965 GHz = 74.4',
+        'bound': 'tensor' if families.get(dominant) == 'tc' else 'fp32', 'kernel': dominant, 'achieved': achieved,
+        'peak': dom['peak_tflops'], 'unit': 'TFLOP/s', 'frac': dom['frac'], 'traffic': traffic,
+        'traffic_source': traffic_src, 'traffic_unit': 'bytes per launch (dram read + write, ncu)',
+        'peak_source': 'fp32: FP32-FMA probe kernel of libtnmf_b200.so timed in this run (MEASURED_PEAKS.json holds no '
+                       'FP32 figure; nominal 148 SM x 128 FMA x 2 x 1.965 GHz = 74.4).  tensor (3xTF32): '
+                       f'{bf16_src} dense bf16 {bf16_peak:.0f} TFLOP/s / 2 (TF32) / 3 (MMAs per product)',
+        'kernels': per_kernel,
         'kernel_ms': kern_ms, 'kernel_launches_per_step': kern_calls,
         'kernel_share_of_step': {k: share[k] / step_ms for k in share},
         'whole_step': {'tflops': flops_step / (step_ms * 1e-3) / 1e12,

@@ -70,6 +70,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self._V_src = None      # the object the caller passes as V ...
         self._V_dev = None      # ... and its device copy
         self._R_buf = None
+        self._H_store = None
         self._ws = None
         self._energy_buf = None
         self._problems = {}
@@ -157,16 +158,18 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         rows are padded to a multiple of 4 elements (16 bytes) - the TMA kernels cut their boxes out of H and need
         that stride alignment - and the returned tensor is the [..., :T_x] view of the padded buffer."""
         pad = (-shape[-1]) % 4
-        if self._dtype != torch.float32 or len(self.atom_shape) != 2 or pad == 0 or self._path == 'generic':
-            if random:
-                return 1 - torch.rand(shape, dtype=self._dtype, device=self.device)
-            return torch.empty(shape, dtype=self._dtype, device=self.device)
+        if self._dtype != torch.float32 or len(self.atom_shape) != 2 or self._path == 'generic':
+            pad = 0
         padded = (*shape[:-1], shape[-1] + pad)
-        buf = torch.rand(padded, dtype=self._dtype, device=self.device) if random else \
-            torch.empty(padded, dtype=self._dtype, device=self.device)
+        # the storage of the previous fit is reused when the shape repeats (fit_stream, repeated fits): a fresh
+        # cudaMalloc of a multi-GB H costs tens of milliseconds
+        buf = self._H_store
+        if buf is None or tuple(buf.shape) != tuple(padded) or buf.dtype != self._dtype:
+            self._H_store = None
+            buf = self._H_store = torch.empty(padded, dtype=self._dtype, device=self.device)
         if random:
-            buf.neg_().add_(1)
-        return buf[..., :shape[-1]]
+            buf.uniform_().neg_().add_(1)       # 1 - U[0, 1), like tnmf/backends/_Backend.py:92
+        return buf[..., :shape[-1]] if pad else buf
 
     def _workspace(self, p: _lib.Problem) -> Tuple[torch.Tensor, int]:
         need = getattr(p, 'ws_need', None)

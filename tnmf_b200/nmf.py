@@ -405,10 +405,20 @@ class _GraphedStep:
         self._launches = 0
 
     def _capture(self, fn):
+        # capture_begin / capture_end on a side stream instead of the `torch.cuda.graph` context manager: the latter
+        # runs gc.collect() and torch.cuda.empty_cache() on entry, which costs about a second with GBs of H cached
+        dev = self._backend.device
         g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         before = self._backend.launches
-        with torch.cuda.graph(g):
-            fn()
+        with torch.cuda.stream(side):
+            g.capture_begin()
+            try:
+                fn()
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream(dev).wait_stream(side)
         self._launches += self._backend.launches - before
         self._backend.launches = before
         return g
