@@ -388,6 +388,27 @@ def test_tc_hupdate_vs_oracle(case, mode):
     _close(Hd, nmf.H, 1e-4)
 
 
+@pytest.mark.parametrize('kw', [dict(), dict(sparsity_H=0.05, inhibition_strength=0.1, cross_atom_inhibition_strength=0.05),
+                                dict(update_W=False), dict(update_H=False)])
+def test_cuda_graph_replay_equals_eager_launches(kw):
+    """fit_batch replays the iteration from CUDA graphs after one eager iteration; the results must be bit-identical to
+    launching every kernel eagerly, for every combination of updates and regularisers, and across repeated fits (which
+    reuse the H storage and re-capture)."""
+    from tnmf_b200 import TransformInvariantNMF
+    rng = np.random.default_rng(77)
+    V = rng.random((6, 3, 40, 56)).astype(np.float32)
+    out = {}
+    for graph in (False, True):
+        nmf = TransformInvariantNMF(n_atoms=16, atom_shape=(7, 7), backend='b200', cuda_graph=graph)
+        for seed in (5, 6):                 # the second fit re-initialises into the same H storage
+            np.random.seed(seed)
+            nmf.fit(V, n_iterations=7, **kw)
+        out[graph] = (nmf.W.copy(), nmf.H.copy(), nmf._energy_function())
+    assert np.array_equal(out[False][0], out[True][0])
+    assert np.array_equal(out[False][1], out[True][1])
+    assert out[False][2] == out[True][2]
+
+
 def test_empty_and_single_sample_batches():
     """Ragged minibatches: an empty slice contributes a zero W gradient, a short last batch is served."""
     rng = np.random.default_rng(7)

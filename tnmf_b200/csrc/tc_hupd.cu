@@ -229,7 +229,7 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
                 }
                 if (sidx + 1 < n_st) load_raw(sidx + 1);             // in flight while this stage is expanded
                 TC_PROF_WAIT(bar, asm volatile("bar.sync 1, 256;\n" ::: "memory"));
-                TC_PROF_WAIT(empty, mbar_wait(&a_empty[st], ph ^ 1u));
+                TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[st], ph ^ 1u, 40));
                 float *d_hi = stages + (size_t)st * p.stage_floats + (size_t)(i >> 3) * 32 + (size_t)(i & 7) * 4 +
                               (size_t)kg0 * (kTile * 4);
                 float *d_lo = d_hi + kTile * KP;
@@ -293,7 +293,7 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
                 const long long gi = g_base + (ty - w.ty0);
                 const int s = (int)(gi & (kSlots - 1));
                 const unsigned par = (unsigned)((gi >> 4) & 1);
-                TC_PROF_WAIT(done, mbar_wait(&row_done[s], par));
+                TC_PROF_WAIT(done, mbar_wait_backoff(&row_done[s], par, 100));
                 tc_fence_after();
                 float neg[kNB], pos[kNB];
                 TC_PROF_WAIT(ldtm, tmem_ld16(tmem_base + lane_base + (unsigned)(s * kNB), neg);

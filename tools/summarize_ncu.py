@@ -19,6 +19,11 @@ METRICS = [
     ('launch__registers_per_thread', 'regs/thread'),
     ('launch__shared_mem_per_block_dynamic', 'dyn smem/block'),
     ('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'FMA pipe active %'),
+    ('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor pipe active % (elapsed)'),
+    ('sm__inst_executed_pipe_tc.sum', 'tcgen05 MMA instructions'),
+    ('l1tex__data_pipe_tc_wavefronts_mem_shared.sum', 'smem wavefronts read by the tensor core'),
+    ('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smem wavefronts LSU (ld + st)'),
+    ('l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'L1/smem throughput %'),
     ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue slots busy %'),
     ('sm__inst_executed.sum.per_cycle_active', 'IPC (SM)'),
     ('smsp__inst_executed.sum', 'warp instructions'),
