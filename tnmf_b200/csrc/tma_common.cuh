@@ -113,6 +113,38 @@ struct Ring {
 
 __device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
+// ---- packed FP32 pairs (sm_100: fma.rn.f32x2 = FFMA2, two FMAs per issue slot) ------------------------------------------
+// A pair lives in one 64-bit register (an aligned register pair).  pk2_fma multiplies a pair by a scalar - ptxas encodes
+// the {w, w} operand as a broadcast selector (R.F32), no duplication is executed.  pk2_make_pinned builds a pair that
+// the compiler must keep (asm volatile): without it ptxas re-creates the shifted window pairs with two MOVs in front of
+// every FFMA2 that uses them, which costs as many issue slots as the packing saves.
+typedef unsigned long long pk2;
+__device__ __forceinline__ pk2 pk2_make(float lo, float hi) {
+    pk2 r;
+    asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ pk2 pk2_make_pinned(float lo, float hi) {
+    pk2 r;
+    asm volatile("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ pk2 pk2_fma(pk2 x, float w, pk2 c) {
+    pk2 d;
+    asm("{\n.reg .b64 t;\nmov.b64 t, {%2, %2};\nfma.rn.f32x2 %0, %1, t, %3;\n}\n" : "=l"(d) : "l"(x), "f"(w), "l"(c));
+    return d;
+}
+__device__ __forceinline__ float pk2_lo(pk2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+    return lo;
+}
+__device__ __forceinline__ float pk2_hi(pk2 v) {
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+    return hi;
+}
+
 // ---- host: tensor maps -------------------------------------------------------------------------------------------
 // Encodes a float32 tiled tensor map: dims / box are listed fastest axis first, strides (bytes) belong to axes 1..rank-1
 // and must be multiples of 16, the base address must be 16-byte aligned.  Out-of-bounds elements read as zero.

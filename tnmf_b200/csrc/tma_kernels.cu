@@ -145,6 +145,10 @@ bool make_hupd_plan(const Geo2 &g, HupdPlan &p) {
     return true;
 }
 
+// Taps of one (atom, channel block) slice of the reconstruction: plain atom rows for RB = 1, pairs over two adjacent
+// atom rows (AY + 1 table rows, zeros past either end) for the packed-FP32 kernels (RB even).
+static int recon_taps_floats(int AY, int AXP, int CB, int RB) { return RB > 1 ? 2 * (AY + 1) * AXP * CB : AY * AXP * CB; }
+
 bool make_recon_plan(const Geo2 &g, ReconPlan &p) {
     p = ReconPlan();
     p.ch = choose_chunk(g.AX);
@@ -156,7 +160,7 @@ bool make_recon_plan(const Geo2 &g, ReconPlan &p) {
     for (; rb >= 1; rb >>= 1) {
         if (rb > 1 && round_up(g.DY, kLY * rb) > g.DY + g.DY / 6) continue;
         p.RB = rb;
-        if (finish_tile_plan(p, g.DY, g.DX, g.AY, rb, 1, g.AY * p.ch.AXP * p.CB)) break;
+        if (finish_tile_plan(p, g.DY, g.DX, g.AY, rb, 1, recon_taps_floats(g.AY, p.ch.AXP, p.CB, rb))) break;
     }
     if (rb < 1) return false;
     p.units = (long long)g.N * p.tiles_y * p.tiles_x * p.nblk;
@@ -253,19 +257,25 @@ __global__ void prepare_taps_hupd_kernel(const float *__restrict__ W, float *__r
     }
 }
 // recon: Wt[m][cb][by][q][c][e] = W[m][cb*CB+c][AY-1-by][AX-1-(4q+e)]   (zero beyond the atom / the channel count)
+// paired (packed-FP32 kernels): Wt[m][cb][t][q][c][e][h] = the same with by = t - h, t = 0..AY, zero for by outside [0, AY)
 __global__ void prepare_taps_recon_kernel(const float *__restrict__ W, float *__restrict__ Wt, int M, int C, int AY,
-                                          int AX, int AXP, int CB, int nblk) {
-    const int total = M * nblk * AY * AXP * CB;
+                                          int AX, int AXP, int CB, int nblk, int paired) {
+    const int rows = paired ? AY + 1 : AY;
+    const int total = M * nblk * rows * AXP * CB * (paired ? 2 : 1);
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         int r = idx;
+        int h = 0;
+        if (paired) { h = r & 1; r >>= 1; }
         const int e = r & 3; r >>= 2;
         const int c = r % CB; r /= CB;
         const int q = r % (AXP >> 2); r /= (AXP >> 2);
-        const int by = r % AY; r /= AY;
+        const int t = r % rows; r /= rows;
         const int cb = r % nblk;
         const int m = r / nblk;
+        const int by = t - h;
         const int ch = cb * CB + c, ax = AX - 1 - (4 * q + e);
-        Wt[idx] = (ch < C && ax >= 0) ? W[(((long long)m * C + ch) * AY + (AY - 1 - by)) * AX + ax] : 0.f;
+        Wt[idx] = (ch < C && ax >= 0 && by >= 0 && by < AY) ? W[(((long long)m * C + ch) * AY + (AY - 1 - by)) * AX + ax]
+                                                            : 0.f;
     }
 }
 
@@ -312,7 +322,7 @@ static size_t taps_region_bytes(const Geo &g) {
     if (make_hupd_plan(q, hp)) bytes = (size_t)g.C * hp.nblk * q.AY * hp.ch.AXP * hp.MB * sizeof(float);
     ReconPlan rp;
     if (make_recon_plan(q, rp)) {
-        const size_t b = (size_t)g.M * rp.nblk * q.AY * rp.ch.AXP * rp.CB * sizeof(float);
+        const size_t b = (size_t)g.M * rp.nblk * recon_taps_floats(q.AY, rp.ch.AXP, rp.CB, rp.RB) * sizeof(float);
         if (b > bytes) bytes = b;
     }
     return align256(bytes);
@@ -356,12 +366,12 @@ int tma_reconstruct(const Geo &g, const float *W, const float *H, float *R, cons
     const Geo2 q = tiled::make_geo2(g);
     ReconPlan p;
     if (!make_recon_plan(q, p)) return TNMF_EUNSUPPORTED;
-    const size_t taps_bytes = (size_t)g.M * p.nblk * q.AY * p.ch.AXP * p.CB * sizeof(float);
+    const size_t taps_bytes = (size_t)g.M * p.nblk * recon_taps_floats(q.AY, p.ch.AXP, p.CB, p.RB) * sizeof(float);
     if (!workspace || workspace_bytes < tma_workspace_bytes(g, TNMF_F32)) return TNMF_EWORKSPACE;
     float *Wt = (float *)workspace;
     const int total = (int)(taps_bytes / sizeof(float));
     prepare_taps_recon_kernel<<<ceil_div(total, 256) < 64 ? ceil_div(total, 256) : 64, 256, 0, st>>>(
-        W, Wt, g.M, g.C, q.AY, q.AX, p.ch.AXP, p.CB, p.nblk);
+        W, Wt, g.M, g.C, q.AY, q.AX, p.ch.AXP, p.CB, p.nblk, p.RB > 1 ? 1 : 0);
     TNMF_CHECK_LAUNCH();
     CUtensorMap mapH;
     int s = map_h(&mapH, q, H, p.pitch, p.HR);

@@ -38,7 +38,8 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
     __syncthreads();
 
     const int units_per_sample = p.tiles_y * p.tiles_x * p.nblk;
-    const int taps_slice = g.AY * p.ch.AXP * CB;                 // floats of one (atom, channel block) slice
+    // floats of one (atom, channel block) slice: plain taps, or (RB even) pairs over two atom rows - see below
+    const int taps_slice = RB > 1 ? 2 * (g.AY + 1) * p.ch.AXP * CB : g.AY * p.ch.AXP * CB;
     const unsigned stage_bytes = (unsigned)((p.pitch * p.HR + taps_slice) * sizeof(float));
     Ring ring;
 
@@ -82,13 +83,28 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
         const int x0 = tx_i * p.tile_x, y0 = ty_i * p.tile_y, c0 = cb * CB;
         const bool warp_active = (y0 + wy * kLY * RB < g.DY) && (x0 + wx * kLX * kCols < g.DX);
 
-        float acc[RB][CB][kCols];
+        // RB even: packed FP32 (FFMA2, fma.rn.f32x2, sm_100).  The two halves of a 64-bit register pair are the same
+        // column of two vertically adjacent output rows (2p, 2p+1); a staged H row hrr reaches them through the atom
+        // rows t = hrr - 2p and t - 1, whose taps prepare_taps_recon stores side by side (zeros past either end), so a
+        // 16-byte load yields two ready-made tap pairs and the window value is a scalar-broadcast operand (R.F32).
+        // One issue slot carries two FMAs and no pack / unpack instruction is executed; the price is one padded atom
+        // row in AY + 1.
+        constexpr int RP = RB > 1 ? RB / 2 : 1;
+        pk2 acc2[RP][CB][kCols];
+        float acc[RB == 1 ? 1 : 1][RB == 1 ? CB : 1][RB == 1 ? kCols : 1];
+        if constexpr (RB > 1) {
 #pragma unroll
-        for (int rr = 0; rr < RB; ++rr)
+            for (int pr = 0; pr < RP; ++pr)
+#pragma unroll
+                for (int c = 0; c < CB; ++c)
+#pragma unroll
+                    for (int j = 0; j < kCols; ++j) acc2[pr][c][j] = 0ull;
+        } else {
 #pragma unroll
             for (int c = 0; c < CB; ++c)
 #pragma unroll
-                for (int j = 0; j < kCols; ++j) acc[rr][c][j] = 0.f;
+                for (int j = 0; j < kCols; ++j) acc[0][c][j] = 0.f;
+        }
 
         for (int m = 0; m < g.M; ++m) {
             mbar_wait(&full_bar[ring.stage], ring.phase);
@@ -105,10 +121,33 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
                             const float4 v = lds128(trow + k * AXC + 4 * q);
                             win[4 * q] = v.x; win[4 * q + 1] = v.y; win[4 * q + 2] = v.z; win[4 * q + 3] = v.w;
                         }
+                        if constexpr (RB > 1) {
 #pragma unroll
-                        for (int rr = 0; rr < RB; ++rr) {
-                            const int by = hrr - rr;
-                            if (by < 0 || by >= g.AY) continue;          // warp-uniform
+                            for (int pr = 0; pr < RP; ++pr) {
+                                const int t = hrr - 2 * pr;                  // pair table row: (atom row t, atom row t - 1)
+                                if (t < 0 || t > g.AY) continue;             // warp-uniform
+                                const float4 *wq = wf + (t * NK + k) * QC * CB * 2;
+#pragma unroll
+                                for (int q = 0; q < QC; ++q) {
+#pragma unroll
+                                    for (int c = 0; c < CB; ++c) {
+                                        const float4 wa = wq[(q * CB + c) * 2], wb = wq[(q * CB + c) * 2 + 1];
+                                        const pk2 t0 = pk2_make(wa.x, wa.y), t1 = pk2_make(wa.z, wa.w);
+                                        const pk2 t2 = pk2_make(wb.x, wb.y), t3 = pk2_make(wb.z, wb.w);
+#pragma unroll
+                                        for (int j = 0; j < kCols; ++j) {
+                                            pk2 sacc = acc2[pr][c][j];
+                                            sacc = pk2_fma(t0, win[4 * q + j], sacc);
+                                            sacc = pk2_fma(t1, win[4 * q + 1 + j], sacc);
+                                            sacc = pk2_fma(t2, win[4 * q + 2 + j], sacc);
+                                            if (!(DROP && q == QC - 1)) sacc = pk2_fma(t3, win[4 * q + 3 + j], sacc);
+                                            acc2[pr][c][j] = sacc;
+                                        }
+                                    }
+                                }
+                            }
+                        } else {
+                            const int by = hrr;
                             const float4 *wq = wf + (by * NK + k) * QC * CB;
 #pragma unroll
                             for (int q = 0; q < QC; ++q) {
@@ -117,12 +156,12 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
                                     const float4 w = wq[q * CB + c];
 #pragma unroll
                                     for (int j = 0; j < kCols; ++j) {
-                                        float s = acc[rr][c][j];
-                                        s = fmaf(w.x, win[4 * q + j], s);
-                                        s = fmaf(w.y, win[4 * q + 1 + j], s);
-                                        s = fmaf(w.z, win[4 * q + 2 + j], s);
-                                        if (!(DROP && q == QC - 1)) s = fmaf(w.w, win[4 * q + 3 + j], s);
-                                        acc[rr][c][j] = s;
+                                        float sacc = acc[0][c][j];
+                                        sacc = fmaf(w.x, win[4 * q + j], sacc);
+                                        sacc = fmaf(w.y, win[4 * q + 1 + j], sacc);
+                                        sacc = fmaf(w.z, win[4 * q + 2 + j], sacc);
+                                        if (!(DROP && q == QC - 1)) sacc = fmaf(w.w, win[4 * q + 3 + j], sacc);
+                                        acc[0][c][j] = sacc;
                                     }
                                 }
                             }
@@ -135,6 +174,11 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
             if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
             ring.advance(n_stages);
         }
+        // value of output row rr, channel c, column j
+        auto out_val = [&](int rr, int c, int j) -> float {
+            if constexpr (RB > 1) return (rr & 1) ? pk2_hi(acc2[rr >> 1][c][j]) : pk2_lo(acc2[rr >> 1][c][j]);
+            else return acc[0][c][j];
+        };
 
         // ---- epilogue of the unit: store R and / or accumulate the energy ----
         const int x = x0 + rx0;
@@ -151,9 +195,9 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
                 if (vec) {
                     if (a.R) {
                         *reinterpret_cast<float4 *>(a.R + base) =
-                            make_float4(acc[rr][c][0], acc[rr][c][1], acc[rr][c][2], acc[rr][c][3]);
+                            make_float4(out_val(rr, c, 0), out_val(rr, c, 1), out_val(rr, c, 2), out_val(rr, c, 3));
                         *reinterpret_cast<float4 *>(a.R + base + 4) =
-                            make_float4(acc[rr][c][4], acc[rr][c][5], acc[rr][c][6], acc[rr][c][7]);
+                            make_float4(out_val(rr, c, 4), out_val(rr, c, 5), out_val(rr, c, 6), out_val(rr, c, 7));
                     }
                     if (a.V) {
                         const float4 v0 = *reinterpret_cast<const float4 *>(a.V + base);
@@ -161,7 +205,7 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
                         const float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
                         for (int j = 0; j < kCols; ++j) {
-                            const double d = (double)vv[j] - (double)acc[rr][c][j];
+                            const double d = (double)vv[j] - (double)out_val(rr, c, j);
                             e_local += d * d;
                         }
                     }
@@ -169,9 +213,9 @@ recon_tma_kernel(const Geo2 g, const ReconPlan p, const __grid_constant__ CUtens
 #pragma unroll
                     for (int j = 0; j < kCols; ++j) {
                         if (x + j < g.DX) {
-                            if (a.R) a.R[base + j] = acc[rr][c][j];
+                            if (a.R) a.R[base + j] = out_val(rr, c, j);
                             if (a.V) {
-                                const double d = (double)a.V[base + j] - (double)acc[rr][c][j];
+                                const double d = (double)a.V[base + j] - (double)out_val(rr, c, j);
                                 e_local += d * d;
                             }
                         }
