@@ -115,18 +115,13 @@ __device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_c
 
 // ---- packed FP32 pairs (sm_100: fma.rn.f32x2 = FFMA2, two FMAs per issue slot) ------------------------------------------
 // A pair lives in one 64-bit register (an aligned register pair).  pk2_fma multiplies a pair by a scalar - ptxas encodes
-// the {w, w} operand as a broadcast selector (R.F32), no duplication is executed.  pk2_make_pinned builds a pair that
-// the compiler must keep (asm volatile): without it ptxas re-creates the shifted window pairs with two MOVs in front of
-// every FFMA2 that uses them, which costs as many issue slots as the packing saves.
+// the {w, w} operand as a broadcast selector (R.F32), no duplication is executed.  Pairs must come out of 8/16-byte
+// loads as they are: a pair assembled from two unrelated registers is re-created by ptxas with two MOVs in front of
+// every FFMA2 that uses it (measured on the reconstruction and on the W gradient: it cancels the packing).
 typedef unsigned long long pk2;
 __device__ __forceinline__ pk2 pk2_make(float lo, float hi) {
     pk2 r;
     asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ pk2 pk2_make_pinned(float lo, float hi) {
-    pk2 r;
-    asm volatile("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
     return r;
 }
 __device__ __forceinline__ pk2 pk2_fma(pk2 x, float w, pk2 c) {
