@@ -81,7 +81,10 @@ def test_tiled_path_selection(lib, monkeypatch):
     assert fam(f32_2d, _lib.OP_GRADIENT_H) == _lib.PATHS['tc']
     assert fam(f32_2d, _lib.OP_RECONSTRUCT) == _lib.PATHS['tiled']
     padded = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, h_pitch=268)
+    assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma'], _lib.PATHS['tc'], _lib.PATHS['tc']]
+    monkeypatch.setenv('TNMF_NO_TC_GRADW', '1')
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma'], _lib.PATHS['tc'], _lib.PATHS['tma']]
+    monkeypatch.delenv('TNMF_NO_TC_GRADW')
     monkeypatch.setenv('TNMF_NO_TC', '1')
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
     monkeypatch.delenv('TNMF_NO_TC')

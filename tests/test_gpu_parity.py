@@ -388,6 +388,38 @@ def test_tc_hupdate_vs_oracle(case, mode):
     _close(Hd, nmf.H, 1e-4)
 
 
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+@pytest.mark.parametrize('case', range(len(TC_CASES)))
+def test_tc_gradient_w_vs_oracle(case, mode):
+    """Tensor-core W gradient (3xTF32, accumulator resident in TMEM, one partial slice per CTA) against the oracle;
+    the sums run over all samples and positions, so the bound is relative to the largest entry."""
+    N, C, M, D, A = TC_CASES[case]
+    rng = np.random.default_rng(400 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    be.reconstruct(Wd, Hd)
+    assert be.kernel_families()['gradient_w'] == 'tc'
+    neg, pos = be.reconstruction_gradient_W(V, Wd, Hd)
+    rn, rp = orc.reconstruction_gradient_W(V64, W64, H64, mode)
+    _close(neg, rn, 2e-5)
+    _close(pos, rp, 2e-5)
+    # on a slice of the samples (minibatch call), and the W update on top of it
+    if N > 2:
+        neg, pos = be.reconstruction_gradient_W(V, Wd, Hd, slice(1, N - 1))
+        rn, rp = orc.reconstruction_gradient_W(V64[1:N - 1], W64, H64[1:N - 1], mode)
+        _close(neg, rn, 2e-5)
+        _close(pos, rp, 2e-5)
+    nmf = orc.OracleNMF(M, A, reconstruction_mode=mode)
+    nmf.V, nmf.W, nmf.H = V64, W64.copy(), H64.copy()
+    nmf.update_W()
+    grad = torch.empty((2, *Wd.shape), dtype=Wd.dtype, device=Wd.device)
+    be.apply_W_update(Wd, be.gradient_W(V, Wd, Hd, slice(None), grad))
+    _close(Wd, nmf.W, 5e-5)
+
+
 @pytest.mark.parametrize('kw', [dict(), dict(sparsity_H=0.05, inhibition_strength=0.1, cross_atom_inhibition_strength=0.05),
                                 dict(update_W=False), dict(update_H=False)])
 def test_cuda_graph_replay_equals_eager_launches(kw):

@@ -339,7 +339,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         kernel; the W gradient always has its finishing reduction)."""
         fam = int(self._lib.tnmf_kernel_family(ctypes.byref(p), op))
         if op == _lib.OP_GRADIENT_W:
-            return 2
+            return (p.n_atoms + 15) // 16 + 1 if fam == _lib.PATHS['tc'] else 2
         if fam == _lib.PATHS['tc']:
             return (p.n_atoms + 15) // 16        # one launch per block of 16 atoms
         return 2 if fam == _lib.PATHS['tma'] else 1
@@ -455,7 +455,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             _lib.check(self._lib.tnmf_gradient_w(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), Hs.data_ptr(),
                                                  out[0].data_ptr(), out[1].data_ptr(), ws.data_ptr(), ws_bytes,
                                                  _stream_ptr(self.device)), 'gradient_w')
-        self.launches += 2
+        self.launches += self._n_launches(p, _lib.OP_GRADIENT_W)
         return out
 
     def apply_W_update(self, W: torch.Tensor, grad: torch.Tensor, eps: float = 1.e-9) -> None:

@@ -50,6 +50,14 @@ bool tc_worthwhile(const Geo &g) {
     return useful >= 0.5 && (long long)g.N * g.T[2] >= 128 && g.A[1] >= 3;
 }
 
+// The tensor-core W gradient stacks the expanded V and R rows into the 128 MMA lanes: 2 * roundup(C*A_x, 8) of them
+// carry taps.  'auto' takes it when that is at least half of the tile (TNMF_NO_TC_GRADW=1 keeps the FP32 kernel).
+bool tc_gradw_worthwhile(const Geo &g) {
+    if (getenv("TNMF_NO_TC") || getenv("TNMF_NO_TC_GRADW")) return false;
+    const int k = g.C * g.A[2], mp = (g.M + 15) / 16 * 16;
+    return 2 * k >= 64 && (double)g.M / mp >= 0.5 && (long long)g.N * g.T[2] >= 64 && g.A[1] >= 3;
+}
+
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;
 // a forced family that cannot serve the problem is an error.
 int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
@@ -57,6 +65,9 @@ int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
     if (p->path == TNMF_PATH_GENERIC) return TNMF_PATH_GENERIC;
     if (op == TNMF_OP_GRADIENT_H && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_worthwhile(g))) &&
         tc_hupd_supported(g, p->dtype))
+        return TNMF_PATH_TC;
+    if (op == TNMF_OP_GRADIENT_W && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_gradw_worthwhile(g))) &&
+        tc_gradw_supported(g, p->dtype))
         return TNMF_PATH_TC;
     bool tma_ok = false;
     if (p->path == TNMF_PATH_AUTO || p->path == TNMF_PATH_TMA || p->path == TNMF_PATH_TC) {
@@ -120,6 +131,10 @@ size_t tnmf_workspace_bytes(const tnmf_problem *p) {
     }
     const size_t t = tma_workspace_bytes(g, p->dtype);
     if (t > bytes) bytes = t;
+    if (tc_gradw_supported(g, p->dtype)) {
+        const size_t w = align256(tc_gradw_workspace_bytes(g));
+        if (w > bytes) bytes = w;
+    }
     return bytes;
 }
 
@@ -274,6 +289,11 @@ int tnmf_gradient_w(const tnmf_problem *p, const void *V, const void *R, const v
     }
     int family = choose_family(p, g, TNMF_OP_GRADIENT_W, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TC) {
+        if (!workspace || workspace_bytes < tnmf_workspace_bytes(p)) return TNMF_EWORKSPACE;
+        return tc_gradient_w(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,
+                             workspace, workspace_bytes, st);
+    }
     if (family == TNMF_PATH_TMA && (!aligned16(V) || !aligned16(R) || !aligned16(H))) {
         if (p->path == TNMF_PATH_TMA) return TNMF_EUNSUPPORTED;
         family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;

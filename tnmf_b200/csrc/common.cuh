@@ -91,6 +91,13 @@ int tc_hupd_launches(const Geo &g);
 int tc_gradient_h(const Geo &g, const float *V, const float *R, const float *W, float *neg, float *pos, float *H,
                   double reg, const float *G, double lambda, const float *Gsum, double lambda_cross, cudaStream_t st);
 
+// ---- implemented in tc_gradw.cu (tcgen05 3xTF32) ------------------------------------------------------------
+bool tc_gradw_supported(const Geo &g, int dtype);
+size_t tc_gradw_workspace_bytes(const Geo &g);
+int tc_gradw_launches(const Geo &g);
+int tc_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
+                  size_t workspace_bytes, cudaStream_t st);
+
 // ---- implemented in elementwise.cu ----------------------------------------------------------------------
 int finish_energy(const double *partials, int n, double *energy, cudaStream_t st);
 template <typename T> int finish_gradient_w(const T *partials, int n_partials, long long count, T *neg, T *pos,

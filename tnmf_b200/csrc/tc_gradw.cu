@@ -1,0 +1,457 @@
+// Tensor-core (tcgen05, 3xTF32) W gradient: a split-K reduction over samples and positions.
+//
+//   neg[m,c,ay,ax] = sum_n sum_{ty,tx} H[n,m,ty,tx] * Vext[n,c,ty-offy+ay,tx-offx+ax]      (tnmf/backends/NumPy.py:77-85)
+//   pos[m,c,ay,ax] = the same with R                                                       (tnmf/backends/NumPy.py:80,87-90)
+//
+// Formulation (the transposed product of tc_hupd.cu).  A CTA owns a tile of 64 activation COLUMNS - column J = n * TXP + xv
+// of the flattened [N x TXP] space, TXP = TX + AX - 1 (gap columns carry zero activations) - and walks down the rows.
+// For a source row r the workers build, once, the expanded rows of V and of R stacked into ONE operand
+//       A'[k', col]   k' = (X, c, ax), X in {V, R}:  A'[.., col] = Xext[n, c, r, xv - offx + ax]         2*KP x 64, K-major
+// and keep the activation rows that meet r, ty = r + offy - ay, in a ring of AY + 1 row tiles
+//       B'[(slot, m), col] = H[n, m, ty(slot), xv]                                                      16 rows per slot
+// One tcgen05.mma (M = 128 lanes of which 2*KP carry taps, N = 16 atoms x live rows, K = 8 columns) then accumulates
+//       D'[k', (ay, m)] += sum_col A'[k', col] * B'[(ay, m), col]
+// for all atom rows of the source row at once; the accumulator (128 lanes x 16*AY columns) stays in TMEM for the whole
+// life of the CTA - numerator in lanes [0, KP), denominator in lanes [KP, 2 KP) - and is written out once as one
+// partial slice per CTA; finish_gradient_w sums the slices in a fixed order in double (deterministic, no atomics).
+// 3xTF32: hi*hi + lo*hi + hi*lo, FP32 accumulation in TMEM.  The tensor core TRUNCATES when it adds into the
+// accumulator (measured: 3e-8 relative bias per accumulation), so a chain is cut after kEpoch source rows: two
+// accumulator sets alternate in TMEM and while one accumulates, the finished one is added (FP32 round-to-nearest) into
+// the CTA's slice in global memory and zeroed.  The MMA reads 128 operand rows; rows past 2*KP alias the
+// following K chunk (finite values, their accumulator lanes are never read).
+//
+// Roles (448 threads): warps 0-7 workers (stage the new activation row into the ring, expand V and R), warps 8 and 9
+// issue the MMAs of the even / odd K steps (converged warps, one elected lane each), warps 10-13 drain the sets.  mbarriers: a_full/a_empty per operand stage, h_full/h_free per ring slot, set_done/set_free per set.
+// Atoms in blocks of 16 (one launch per block).  Bound: tensor pipe at the TF32 rate / 3 with 2*KP/128 useful lanes.
+#include <cstdlib>
+#include "tc_common.cuh"
+
+namespace tnmf {
+namespace tc {
+
+using tiled::ceil_div;
+using tiled::Geo2;
+using tiled::round_up;
+
+namespace gw {
+
+constexpr int kCT = 64;             // activation columns per tile = contraction length of one source row
+constexpr int kNB = 16;             // atoms per launch
+constexpr int kWorkers = 256;
+constexpr int kThreads = 32 * 14;     // 8 workers + 2 MMA issuers + 4 accumulator drainers
+#ifndef TNMF_GW_EPOCH
+#define TNMF_GW_EPOCH 8
+#endif
+#ifndef TNMF_GW_ISSUERS
+#define TNMF_GW_ISSUERS 2
+#endif
+constexpr int kEpoch = TNMF_GW_EPOCH;  // source rows accumulated into one TMEM set before it is drained
+constexpr int kIssuers = TNMF_GW_ISSUERS;
+constexpr int kMaxStages = 4;
+constexpr int kMaxSmem = 226 * 1024;
+constexpr int kRawMax = 4;          // raw elements per worker and tensor pair: 2 * C * (64 + AX - 1) <= 1024
+constexpr int kChunkMax = 8;        // 16-byte chunks of an operand stage per worker: 2 * KP * 16 <= 2048
+
+struct Plan {
+    int KP, TXP, RW, raw_floats, nraw, nchunk;
+    int RS, NRr;                    // ring slots (AY + 1), ring rows (16 per slot)
+    int ring_floats, stage_floats;  // floats of ONE of the hi / lo halves
+    int tiles, rblocks, rows_per_block;
+    long long units;
+    int n_stages, grid;
+    size_t smem;
+};
+
+struct Args {
+    const float *V, *R, *H;
+    float *partials;                // [grid][2][M*C*AY*AX]
+    int m0;
+};
+
+bool make_plan(const Geo2 &g, Plan &p) {
+    p = Plan();
+    if (g.AY < 1 || g.AY > 15) return false;
+    p.KP = round_up(g.C * g.AX, 8);
+    if (2 * p.KP > 128) return false;
+    p.TXP = g.TX + g.AX - 1;
+    p.RW = kCT + g.AX - 1;
+    p.raw_floats = round_up(g.C * p.RW + kCT + 8, 32);      // + zeros read by the padded k
+    p.nraw = ceil_div(2 * g.C * p.RW, kWorkers);
+    if (p.nraw > kRawMax) return false;
+    p.nchunk = ceil_div(2 * p.KP * (kCT / 4), kWorkers);
+    if (p.nchunk > kChunkMax) return false;
+    p.RS = g.AY + 1;
+    p.NRr = p.RS * kNB;
+    p.ring_floats = p.NRr * kCT;
+    p.stage_floats = 2 * p.KP * kCT;
+    const size_t fixed = (size_t)2 * p.ring_floats * 4 + (size_t)8 * p.raw_floats * 4 + 4096;   // + over-read pad
+    if (fixed + 2 * (size_t)2 * p.stage_floats * 4 > (size_t)kMaxSmem) return false;
+    p.n_stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)2 * p.stage_floats * 4));
+    if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
+    p.smem = fixed + (size_t)p.n_stages * 2 * p.stage_floats * 4;
+    const long long cols = (long long)g.N * p.TXP;
+    if (cols <= 0 || cols >= (1ll << 31) - kCT) return false;
+    p.tiles = (int)((cols + kCT - 1) / kCT);
+    const int sms = tma::sm_count();
+    double best = -1;
+    for (int rb = 1; rb <= g.TY && rb <= 64; ++rb) {
+        const int rows = ceil_div(g.TY, rb);
+        if (ceil_div(g.TY, rows) != rb) continue;
+        const long long units = (long long)p.tiles * rb;
+        const double waves = (double)((units + sms - 1) / sms);
+        const double cost = waves * (rows + 0.5 * (g.AY - 1) + 1.0);
+        if (best < 0 || cost < best * 0.999) { best = cost; p.rblocks = rb; p.rows_per_block = rows; }
+    }
+    p.units = (long long)p.tiles * p.rblocks;
+    p.grid = (int)(p.units < sms ? p.units : sms);
+    return true;
+}
+
+struct Unit {
+    int tile, ty0, ty1, r_lo, r_hi;
+};
+__device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan &p) {
+    Unit w;
+    const int rb = (int)(u / p.tiles);
+    w.tile = (int)(u - (long long)rb * p.tiles);
+    w.ty0 = rb * p.rows_per_block;
+    w.ty1 = min(g.TY, w.ty0 + p.rows_per_block);
+    w.r_lo = max(0, w.ty0 - g.offy);
+    w.r_hi = min(g.DY - 1, w.ty1 - 1 - g.offy + g.AY - 1);
+    return w;
+}
+
+__device__ __forceinline__ void tmem_st16_zero(unsigned addr) {
+    const unsigned z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::
+            "r"(addr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, const Plan p, const Args a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long a_full[kMaxStages], a_empty[kMaxStages], h_full[16], h_free[16], set_done[2],
+        set_free[2];
+    __shared__ unsigned tmem_base_s;
+    __shared__ __align__(16) int koff[64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KP = p.KP, AY = g.AY, AX = g.AX, C = g.C, RS = p.RS, RW = p.RW;
+    float *ring_hi = smem, *ring_lo = smem + p.ring_floats;
+    float *raw = ring_lo + p.ring_floats;                       // [2 buffers][hi, lo][V, R][raw_floats]
+    float *stages = raw + 8 * p.raw_floats;                     // [stage][hi, lo][stage_floats]
+
+    if (tid == 0) {
+        for (int s = 0; s < p.n_stages; ++s) { mbar_init(&a_full[s], kWorkers); mbar_init(&a_empty[s], kIssuers); }
+        for (int s = 0; s < 16; ++s) { mbar_init(&h_full[s], kWorkers); mbar_init(&h_free[s], kIssuers); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&set_done[s], kIssuers); mbar_init(&set_free[s], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(&tmem_base_s, 512);
+    if (tid < KP) koff[tid] = tid < C * AX ? (tid / AX) * RW + (tid % AX) : C * RW;
+    // zeros behind every raw array (read through the padded k) - written once
+    for (int idx = tid; idx < 8 * (kCT + 8); idx += kThreads) raw[(idx / (kCT + 8)) * p.raw_floats + C * RW + (idx % (kCT + 8))] = 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = tmem_base_s;
+    if (warp < 4) {                                             // accumulator = 0
+        for (int c = 0; c < 512; c += 16) tmem_st16_zero(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c);
+        tmem_st_wait();
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const long long count = (long long)g.M * C * AY * AX;
+
+    if (warp < 8) {
+        // ------------------------------------ workers ------------------------------------
+        int st = 0;
+        unsigned ph = 0, buf = 0;
+        const long long plane = (long long)g.DY * g.DX;
+        const int raw_count = 2 * C * RW;
+        // operand chunks of this thread: q = tid + 256 e -> (column group cg, operand row); fixed for the kernel
+        int c_src[kChunkMax], c_dst[kChunkMax];
+#pragma unroll
+        for (int e = 0; e < kChunkMax; ++e) {
+            const int q = tid + kWorkers * e;
+            c_src[e] = -1;
+            c_dst[e] = 0;
+            if (e < p.nchunk && q < 2 * KP * (kCT / 4)) {
+                const int cg = q / (2 * KP), row = q - cg * (2 * KP);
+                const int X = row >= KP ? 1 : 0, k = row - X * KP;
+                c_src[e] = X * p.raw_floats + koff[k] + 4 * cg;
+                c_dst[e] = (row >> 3) * 32 + cg * (2 * KP * 4) + (row & 7) * 4;
+            }
+        }
+        // activation chunk of this thread: atom ml, columns 4 cg .. 4 cg + 3 of the tile
+        const int h_ml = tid >> 4, h_cg = tid & 15;
+        long long g_base = 0;
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit w = make_unit(u, g, p);
+            // source element of every raw slot (q = tid + 256 e -> tensor, channel, position) in row 0, or -1: zero
+            long long roff[kRawMax];
+#pragma unroll
+            for (int e = 0; e < kRawMax; ++e) {
+                roff[e] = -1;
+                const int q = tid + kWorkers * e;
+                if (e < p.nraw && q < raw_count) {
+                    const int X = q >= C * RW ? 1 : 0, qq = q - X * C * RW;
+                    const int c = qq / RW;
+                    const long long J = (long long)w.tile * kCT + (qq - c * RW);
+                    const int n = (int)(J / p.TXP);
+                    const int x = (int)(J - (long long)n * p.TXP) - g.offx;
+                    if (n < g.N && (unsigned)x < (unsigned)g.DX) roff[e] = ((long long)n * C + c) * plane + x;
+                }
+            }
+            // activations: element offsets of the 4 columns in row 0 of atom m0 + ml, or -1: zero (gap column, no atom)
+            long long hoff[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long J = (long long)w.tile * kCT + 4 * h_cg + e;
+                const int n = (int)(J / p.TXP);
+                const int xv = (int)(J - (long long)n * p.TXP);
+                hoff[e] = (n < g.N && xv < g.TX && a.m0 + h_ml < g.M)
+                              ? (long long)n * g.hsn + (long long)(a.m0 + h_ml) * g.hsm + xv : -1;
+            }
+            float rv[kRawMax];
+            auto load_raw = [&](int r) {
+                const long long row = (long long)r * g.DX;
+#pragma unroll
+                for (int e = 0; e < kRawMax; ++e) {
+                    const float *src = (tid + kWorkers * e >= C * RW) ? a.R : a.V;
+                    rv[e] = roff[e] >= 0 ? __ldg(src + row + roff[e]) : 0.f;
+                }
+            };
+            // activation row fetch, issued one source row ahead of its use (interior rows bring exactly one new row)
+            auto load_h = [&](int ty) {
+                float4 hv;
+                hv.x = hoff[0] >= 0 ? a.H[hoff[0] + (long long)ty * g.hsy] : 0.f;
+                hv.y = hoff[1] >= 0 ? a.H[hoff[1] + (long long)ty * g.hsy] : 0.f;
+                hv.z = hoff[2] >= 0 ? a.H[hoff[2] + (long long)ty * g.hsy] : 0.f;
+                hv.w = hoff[3] >= 0 ? a.H[hoff[3] + (long long)ty * g.hsy] : 0.f;
+                return hv;
+            };
+            float4 hv_next = make_float4(0.f, 0.f, 0.f, 0.f);
+            int hv_row = -1;
+            int next_new = w.ty0;
+            load_raw(w.r_lo);
+            for (int r = w.r_lo; r <= w.r_hi; ++r) {
+                // ---- activation rows that enter the window with this source row ----
+                const int t_b = min(w.ty1 - 1, r + g.offy);
+                for (; next_new <= t_b; ++next_new) {
+                    const long long gi = g_base + (next_new - w.ty0);
+                    const int slot = (int)(gi % RS);
+                    const float4 hv = next_new == hv_row ? hv_next : load_h(next_new);
+                    if (gi >= RS) mbar_wait_backoff(&h_free[slot], (unsigned)(((gi / RS) - 1) & 1), 40);
+                    float4 hi, lo;
+                    split_tf32(hv.x, hi.x, lo.x); split_tf32(hv.y, hi.y, lo.y);
+                    split_tf32(hv.z, hi.z, lo.z); split_tf32(hv.w, hi.w, lo.w);
+                    const int nrow = slot * kNB + h_ml;
+                    const size_t o = (size_t)(nrow >> 3) * 32 + (size_t)h_cg * (p.NRr * 4) + (size_t)(nrow & 7) * 4;
+                    *reinterpret_cast<float4 *>(ring_hi + o) = hi;
+                    *reinterpret_cast<float4 *>(ring_lo + o) = lo;
+                    fence_proxy_async();
+                    mbar_arrive(&h_full[slot]);
+                }
+                // ---- expanded V and R rows ----
+                float *raw_hi = raw + (size_t)buf * 4 * p.raw_floats, *raw_lo = raw_hi + 2 * p.raw_floats;
+#pragma unroll
+                for (int e = 0; e < kRawMax; ++e) {
+                    const int q = tid + kWorkers * e;
+                    if (e < p.nraw && q < raw_count) {
+                        float hi, lo;
+                        split_tf32(rv[e], hi, lo);
+                        const int X = q >= C * RW ? 1 : 0;
+                        raw_hi[X * p.raw_floats + (q - X * C * RW)] = hi;
+                        raw_lo[X * p.raw_floats + (q - X * C * RW)] = lo;
+                    }
+                }
+                if (r < w.r_hi) load_raw(r + 1);                      // in flight while this row is expanded
+                if (next_new < w.ty1) { hv_next = load_h(next_new); hv_row = next_new; }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                mbar_wait_backoff(&a_empty[st], ph ^ 1u, 40);
+                float *d_hi = stages + (size_t)st * 2 * p.stage_floats, *d_lo = d_hi + p.stage_floats;
+#pragma unroll
+                for (int e = 0; e < kChunkMax; ++e) {
+                    if (c_src[e] >= 0) {
+                        const float *sh = raw_hi + c_src[e], *sl = raw_lo + c_src[e];
+                        *reinterpret_cast<float4 *>(d_hi + c_dst[e]) = make_float4(sh[0], sh[1], sh[2], sh[3]);
+                        *reinterpret_cast<float4 *>(d_lo + c_dst[e]) = make_float4(sl[0], sl[1], sl[2], sl[3]);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&a_full[st]);
+                if (++st == p.n_stages) { st = 0; ph ^= 1u; }
+                buf ^= 1u;
+            }
+            g_base += w.ty1 - w.ty0;
+        }
+    } else if (warp >= 10) {
+        // ------------------------------------ accumulator drainers ------------------------------------
+        // one accumulator set per epoch: lane = operand row k' = (X, c, ax), column = (ay, atom)
+        long long rows_done = 0;
+        bool first_drain = true;
+        auto drain = [&](long long e) {
+            const int set = (int)(e & 1);
+            mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100);
+            tc_fence_after();
+            const int l = (warp & 3) * 32 + lane;
+            const int X = l >= KP ? 1 : 0, k = l - X * KP;
+            const bool live = l < 2 * KP && k < C * AX;
+            const int c = live ? k / AX : 0, ax = live ? k - c * AX : 0;
+            float *slice = a.partials + (long long)blockIdx.x * 2 * count + (long long)X * count;
+            const unsigned tbase = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(set * 256);
+            for (int j = 0; j < AY; ++j) {
+                float v[16];
+                tmem_ld16(tbase + (unsigned)(j * kNB), v);
+                tmem_ld_wait();
+                tmem_st16_zero(tbase + (unsigned)(j * kNB));
+                const int ay = AY - 1 - j;
+                if (live) {
+                    // all 16 running sums are fetched before the first store (stores would otherwise order the loads)
+                    float *dst0 = slice + (((long long)a.m0 * C + c) * AY + ay) * AX + ax;
+                    const long long mstride = (long long)C * AY * AX;
+                    float old[kNB];
+#pragma unroll
+                    for (int ml = 0; ml < kNB; ++ml)
+                        old[ml] = (!first_drain && a.m0 + ml < g.M) ? __ldcg(dst0 + ml * mstride) : 0.f;
+#pragma unroll
+                    for (int ml = 0; ml < kNB; ++ml)
+                        if (a.m0 + ml < g.M) __stcg(dst0 + ml * mstride, v[ml] + old[ml]);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&set_free[set]);
+            first_drain = false;
+        };
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit w = make_unit(u, g, p);
+            rows_done += w.r_hi - w.r_lo + 1;
+        }
+        const long long n_epochs = (rows_done + kEpoch - 1) / kEpoch;
+        for (long long e = 0; e < n_epochs; ++e) drain(e);
+    } else if (warp - 8 < kIssuers) {
+        // ------------------------------------ MMA issuers (converged warps, one elected lane each) ------------------------------------
+        const unsigned lbo_a = (unsigned)(2 * KP) * 16, lbo_b = (unsigned)p.NRr * 16;
+        const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
+        const unsigned a_lo_word = ((lbo_a >> 4) << 16), b_lo_word = ((lbo_b >> 4) << 16);
+        const unsigned ring16[3] = {smem_u32(ring_hi) >> 4, smem_u32(ring_hi) >> 4, smem_u32(ring_lo) >> 4};
+        const unsigned stage_addr0 = smem_u32(stages);
+        const unsigned a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
+        const int x = warp - 8;                 // warp 8 issues the even K steps, warp 9 the odd ones
+        int st = 0;
+        unsigned ph = 0;
+        long long g_base = 0, rows_done = 0;
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit w = make_unit(u, g, p);
+            int next_new = w.ty0, next_out = w.ty0;
+            for (int r = w.r_lo; r <= w.r_hi; ++r) {
+                const long long epoch = rows_done / kEpoch;
+                if (rows_done % kEpoch == 0 && epoch >= 2) {
+                    mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1));
+                    tc_fence_after();
+                }
+                const unsigned tset = tmem_base + (unsigned)((epoch & 1) * 256);
+                const int ay_lo = max(0, r + g.offy - (w.ty1 - 1)), ay_hi = min(AY - 1, r + g.offy - w.ty0);
+                const int t_a = r + g.offy - ay_hi, t_b = r + g.offy - ay_lo;
+                const int j0 = r + g.offy - AY + 1;                 // activation row of accumulator column block 0
+                for (; next_new <= t_b; ++next_new) {
+                    const long long gi = g_base + (next_new - w.ty0);
+                    mbar_wait(&h_full[gi % RS], (unsigned)((gi / RS) & 1));
+                }
+                mbar_wait(&a_full[st], ph);
+                tc_fence_after();
+                // the window [t_a, t_b] in ring order: at most two runs of slots
+                unsigned o_col[2], o_idesc[2], o_b16[2];
+                int n_ops = 0;
+                {
+                    const int cnt = t_b - t_a + 1;
+                    const int s = (int)((g_base + (t_a - w.ty0)) % RS);
+                    const int first = min(cnt, RS - s);
+                    o_col[0] = (unsigned)((t_a - j0) * kNB); o_idesc[0] = idesc_tf32(128, kNB * first);
+                    o_b16[0] = (unsigned)s * 16u; n_ops = 1;
+                    if (cnt > first) {
+                        o_col[1] = (unsigned)((t_a - j0 + first) * kNB); o_idesc[1] = idesc_tf32(128, kNB * (cnt - first));
+                        o_b16[1] = 0u; n_ops = 2;
+                    }
+                }
+                const unsigned a_hi16 = (stage_addr0 + (unsigned)st * 2u * (unsigned)p.stage_floats * 4u) >> 4;
+                const unsigned a_addr16[3] = {a_hi16, a_hi16 + (((unsigned)p.stage_floats * 4u) >> 4), a_hi16};
+                for (int ks = x; ks < kCT / 8; ks += kIssuers) {
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        const unsigned long long da =
+                            ((unsigned long long)desc_hi << 32) | (a_lo_word | (a_addr16[t] + ks * a_step16));
+                        const unsigned b16 = ring16[t] + ks * b_step16;
+                        mma_tf32_elect(tset + o_col[0], da,
+                                       ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[0])), o_idesc[0], 1u);
+                        if (n_ops > 1)
+                            mma_tf32_elect(tset + o_col[1], da,
+                                           ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[1])), o_idesc[1],
+                                           1u);
+                    }
+                }
+                mma_commit_elect(&a_empty[st]);
+                if (++st == p.n_stages) { st = 0; ph ^= 1u; }
+                // activation rows that leave the window: their slots may be overwritten once these MMAs are done
+                for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r; ++next_out)
+                    mma_commit_elect(&h_free[(g_base + (next_out - w.ty0)) % RS]);
+                if (++rows_done % kEpoch == 0) mma_commit_elect(&set_done[epoch & 1]);
+            }
+            g_base += w.ty1 - w.ty0;
+        }
+        if (rows_done % kEpoch != 0) mma_commit_elect(&set_done[(rows_done / kEpoch) & 1]);
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace gw
+}  // namespace tc
+
+// ---- dispatch ----------------------------------------------------------------------------------------------------------
+bool tc_gradw_supported(const Geo &g, int dtype) {
+    if (dtype != TNMF_F32 || g.wrap) return false;
+    if (g.D[0] != 1 || g.A[0] != 1 || g.T[0] != 1) return false;      // rank <= 2
+    if (g.D[1] == 1 && g.A[1] == 1) return false;                     // rank 1: the FP32 kernels serve it
+    if (g.N < 1) return false;
+    tc::gw::Plan p;
+    return tc::gw::make_plan(tiled::make_geo2(g), p);
+}
+
+size_t tc_gradw_workspace_bytes(const Geo &g) {
+    tc::gw::Plan p;
+    if (!tc::gw::make_plan(tiled::make_geo2(g), p)) return 0;
+    return (size_t)p.grid * 2 * (size_t)g.M * g.C * g.A[1] * g.A[2] * sizeof(float);
+}
+
+int tc_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
+                  size_t workspace_bytes, cudaStream_t st) {
+    const tiled::Geo2 q = tiled::make_geo2(g);
+    tc::gw::Plan p;
+    if (!tc::gw::make_plan(q, p)) return TNMF_EUNSUPPORTED;
+    const long long count = (long long)g.M * g.C * g.A[1] * g.A[2];
+    if (!workspace || workspace_bytes < tc_gradw_workspace_bytes(g)) return TNMF_EWORKSPACE;
+    cudaError_t e = cudaFuncSetAttribute(tc::gw::gradw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc::gw::kMaxSmem);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    tc::gw::Args a;
+    a.V = V; a.R = R; a.H = H; a.partials = (float *)workspace;
+    for (int m0 = 0; m0 < g.M; m0 += tc::gw::kNB) {
+        a.m0 = m0;
+        tc::gw::gradw_tc_kernel<<<(unsigned)p.grid, tc::gw::kThreads, p.smem, st>>>(q, p, a);
+        TNMF_CHECK_LAUNCH();
+    }
+    return finish_gradient_w<float>((const float *)workspace, p.grid, count, neg, pos, st);
+}
+
+int tc_gradw_launches(const Geo &g) { return tiled::ceil_div(g.M, tc::gw::kNB) + 1; }
+
+}  // namespace tnmf

@@ -132,11 +132,13 @@ __device__ __forceinline__ pk2 pk2_fma(pk2 x, float w, pk2 c) {
 __device__ __forceinline__ float pk2_lo(pk2 v) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+    (void)hi;
     return lo;
 }
 __device__ __forceinline__ float pk2_hi(pk2 v) {
     float lo, hi;
     asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+    (void)lo;
     return hi;
 }
 
