@@ -11,6 +11,16 @@
 #include <cstdint>
 #include "tma_common.cuh"
 
+// -DTNMF_TC_PROFILE: CTA 0 prints, per role, the cycles it spent blocked on each of its barriers (debug builds only)
+#ifdef TNMF_TC_PROFILE
+#include <cstdio>
+#define TC_PROF_DECL(n) long long prof_##n = 0
+#define TC_PROF_WAIT(n, stmt) do { const long long t__ = clock64(); stmt; prof_##n += clock64() - t__; } while (0)
+#else
+#define TC_PROF_DECL(n)
+#define TC_PROF_WAIT(n, stmt) stmt
+#endif
+
 namespace tnmf {
 namespace tc {
 

@@ -35,16 +35,16 @@ using tiled::round_up;
 
 namespace gw {
 
-constexpr int kCT = 64;             // activation columns per tile = contraction length of one source row
-constexpr int kNB = 16;             // atoms per launch
-constexpr int kWorkers = 256;
-constexpr int kThreads = 32 * 14;     // 8 workers + 2 MMA issuers + 4 accumulator drainers
 #ifndef TNMF_GW_EPOCH
 #define TNMF_GW_EPOCH 8
 #endif
 #ifndef TNMF_GW_ISSUERS
 #define TNMF_GW_ISSUERS 2
 #endif
+constexpr int kCT = 64;             // activation columns per tile = contraction length of one source row
+constexpr int kNB = 16;             // atoms per launch
+constexpr int kWorkers = 256;
+constexpr int kThreads = 32 * (8 + TNMF_GW_ISSUERS + 4);   // 8 workers + MMA issuers + 4 accumulator drainers
 constexpr int kEpoch = TNMF_GW_EPOCH;  // source rows accumulated into one TMEM set before it is drained
 constexpr int kIssuers = TNMF_GW_ISSUERS;
 constexpr int kMaxStages = 4;
@@ -80,12 +80,17 @@ bool make_plan(const Geo2 &g, Plan &p) {
     if (p.nraw > kRawMax) return false;
     p.nchunk = ceil_div(2 * p.KP * (kCT / 4), kWorkers);
     if (p.nchunk > kChunkMax) return false;
-    p.RS = g.AY + 1;
-    p.NRr = p.RS * kNB;
-    p.ring_floats = p.NRr * kCT;
     p.stage_floats = 2 * p.KP * kCT;
-    const size_t fixed = (size_t)2 * p.ring_floats * 4 + (size_t)8 * p.raw_floats * 4 + 4096;   // + over-read pad
-    if (fixed + 2 * (size_t)2 * p.stage_floats * 4 > (size_t)kMaxSmem) return false;
+    // ring slots: AY + 1 at least; more (up to 16) while two operand stages still fit - a longer ring splits fewer
+    // live-row windows at its wrap-around, and every split costs an extra MMA on the 46-clk issue floor
+    size_t fixed = 0;
+    for (p.RS = 16; p.RS >= g.AY + 1; --p.RS) {
+        p.NRr = p.RS * kNB;
+        p.ring_floats = p.NRr * kCT;
+        fixed = (size_t)2 * p.ring_floats * 4 + (size_t)8 * p.raw_floats * 4 + 4096;   // + over-read pad
+        if (fixed + 2 * (size_t)2 * p.stage_floats * 4 <= (size_t)kMaxSmem) break;
+    }
+    if (p.RS < g.AY + 1) return false;
     p.n_stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)2 * p.stage_floats * 4));
     if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
     p.smem = fixed + (size_t)p.n_stages * 2 * p.stage_floats * 4;
@@ -171,6 +176,10 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         // ------------------------------------ workers ------------------------------------
         int st = 0;
         unsigned ph = 0, buf = 0;
+        TC_PROF_DECL(empty); TC_PROF_DECL(hfree); TC_PROF_DECL(bar); TC_PROF_DECL(total); TC_PROF_DECL(hst); TC_PROF_DECL(rawp); TC_PROF_DECL(exp);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         const long long plane = (long long)g.DY * g.DX;
         const int raw_count = 2 * C * RW;
         // operand chunks of this thread: q = tid + 256 e -> (column group cg, operand row); fixed for the kernel
@@ -242,11 +251,15 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
             for (int r = w.r_lo; r <= w.r_hi; ++r) {
                 // ---- activation rows that enter the window with this source row ----
                 const int t_b = min(w.ty1 - 1, r + g.offy);
+                unsigned new_slots = 0;
                 for (; next_new <= t_b; ++next_new) {
                     const long long gi = g_base + (next_new - w.ty0);
                     const int slot = (int)(gi % RS);
                     const float4 hv = next_new == hv_row ? hv_next : load_h(next_new);
-                    if (gi >= RS) mbar_wait_backoff(&h_free[slot], (unsigned)(((gi / RS) - 1) & 1), 40);
+                    if (gi >= RS) TC_PROF_WAIT(hfree, mbar_wait_backoff(&h_free[slot], (unsigned)(((gi / RS) - 1) & 1), 40));
+#ifdef TNMF_TC_PROFILE
+                    const long long t_h = clock64();
+#endif
                     float4 hi, lo;
                     split_tf32(hv.x, hi.x, lo.x); split_tf32(hv.y, hi.y, lo.y);
                     split_tf32(hv.z, hi.z, lo.z); split_tf32(hv.w, hi.w, lo.w);
@@ -254,9 +267,14 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                     const size_t o = (size_t)(nrow >> 3) * 32 + (size_t)h_cg * (p.NRr * 4) + (size_t)(nrow & 7) * 4;
                     *reinterpret_cast<float4 *>(ring_hi + o) = hi;
                     *reinterpret_cast<float4 *>(ring_lo + o) = lo;
-                    fence_proxy_async();
-                    mbar_arrive(&h_full[slot]);
+                    new_slots |= 1u << slot;                            // published below, behind one proxy fence
+#ifdef TNMF_TC_PROFILE
+                    prof_hst += clock64() - t_h;
+#endif
                 }
+#ifdef TNMF_TC_PROFILE
+                const long long t_r = clock64();
+#endif
                 // ---- expanded V and R rows ----
                 float *raw_hi = raw + (size_t)buf * 4 * p.raw_floats, *raw_lo = raw_hi + 2 * p.raw_floats;
 #pragma unroll
@@ -272,8 +290,14 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                 }
                 if (r < w.r_hi) load_raw(r + 1);                      // in flight while this row is expanded
                 if (next_new < w.ty1) { hv_next = load_h(next_new); hv_row = next_new; }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
-                mbar_wait_backoff(&a_empty[st], ph ^ 1u, 40);
+#ifdef TNMF_TC_PROFILE
+                prof_rawp += clock64() - t_r;
+#endif
+                TC_PROF_WAIT(bar, asm volatile("bar.sync 1, 256;\n" ::: "memory"));
+                TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[st], ph ^ 1u, 40));
+#ifdef TNMF_TC_PROFILE
+                const long long t_e = clock64();
+#endif
                 float *d_hi = stages + (size_t)st * 2 * p.stage_floats, *d_lo = d_hi + p.stage_floats;
 #pragma unroll
                 for (int e = 0; e < kChunkMax; ++e) {
@@ -284,13 +308,23 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                     }
                 }
                 fence_proxy_async();
+                for (; new_slots; new_slots &= new_slots - 1) mbar_arrive(&h_full[__ffs(new_slots) - 1]);
                 mbar_arrive(&a_full[st]);
+#ifdef TNMF_TC_PROFILE
+                prof_exp += clock64() - t_e;
+#endif
                 if (++st == p.n_stages) { st = 0; ph ^= 1u; }
                 buf ^= 1u;
             }
             g_base += w.ty1 - w.ty0;
         }
-    } else if (warp >= 10) {
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && tid == 0)
+            printf("gradw workers: total %lld  wait a_empty %lld  wait h_free %lld  raw barrier %lld  h staging %lld  raw %lld  "
+                   "expansion %lld\n", prof_total, prof_empty, prof_hfree, prof_bar, prof_hst, prof_rawp, prof_exp);
+#endif
+    } else if (warp >= 8 + kIssuers) {
         // ------------------------------------ accumulator drainers ------------------------------------
         // one accumulator set per epoch: lane = operand row k' = (X, c, ax), column = (ay, atom)
         long long rows_done = 0;
@@ -335,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         }
         const long long n_epochs = (rows_done + kEpoch - 1) / kEpoch;
         for (long long e = 0; e < n_epochs; ++e) drain(e);
-    } else if (warp - 8 < kIssuers) {
+    } else {
         // ------------------------------------ MMA issuers (converged warps, one elected lane each) ------------------------------------
         const unsigned lbo_a = (unsigned)(2 * KP) * 16, lbo_b = (unsigned)p.NRr * 16;
         const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
@@ -347,13 +381,17 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         int st = 0;
         unsigned ph = 0;
         long long g_base = 0, rows_done = 0;
+        TC_PROF_DECL(full); TC_PROF_DECL(hfull); TC_PROF_DECL(setfree); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             int next_new = w.ty0, next_out = w.ty0;
             for (int r = w.r_lo; r <= w.r_hi; ++r) {
                 const long long epoch = rows_done / kEpoch;
                 if (rows_done % kEpoch == 0 && epoch >= 2) {
-                    mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1));
+                    TC_PROF_WAIT(setfree, mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1)));
                     tc_fence_after();
                 }
                 const unsigned tset = tmem_base + (unsigned)((epoch & 1) * 256);
@@ -362,9 +400,9 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                 const int j0 = r + g.offy - AY + 1;                 // activation row of accumulator column block 0
                 for (; next_new <= t_b; ++next_new) {
                     const long long gi = g_base + (next_new - w.ty0);
-                    mbar_wait(&h_full[gi % RS], (unsigned)((gi / RS) & 1));
+                    TC_PROF_WAIT(hfull, mbar_wait(&h_full[gi % RS], (unsigned)((gi / RS) & 1)));
                 }
-                mbar_wait(&a_full[st], ph);
+                TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
                 tc_fence_after();
                 // the window [t_a, t_b] in ring order: at most two runs of slots
                 unsigned o_col[2], o_idesc[2], o_b16[2];
@@ -406,6 +444,12 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
             g_base += w.ty1 - w.ty0;
         }
         if (rows_done % kEpoch != 0) mma_commit_elect(&set_done[(rows_done / kEpoch) & 1]);
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && lane == 0 && x == 0)
+            printf("gradw mma: total %lld  wait a_full %lld  wait h_full %lld  wait set_free %lld\n", prof_total, prof_full,
+                   prof_hfull, prof_setfree);
+#endif
         __syncwarp();
     }
     tc_fence_before();
