@@ -86,7 +86,7 @@ bool make_plan(const Geo2 &g, Plan &p) {
     size_t fixed = 0;
     for (p.RS = 16; p.RS >= g.AY + 1; --p.RS) {
         p.NRr = p.RS * kNB;
-        p.ring_floats = p.NRr * kCT;
+        p.ring_floats = (p.NRr * 4 + 4) * (kCT / 4);        // K-chunk stride padded by 16 bytes: conflict-free row staging
         fixed = (size_t)2 * p.ring_floats * 4 + (size_t)8 * p.raw_floats * 4 + 4096;   // + over-read pad
         if (fixed + 2 * (size_t)2 * p.stage_floats * 4 <= (size_t)kMaxSmem) break;
     }
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                     split_tf32(hv.x, hi.x, lo.x); split_tf32(hv.y, hi.y, lo.y);
                     split_tf32(hv.z, hi.z, lo.z); split_tf32(hv.w, hi.w, lo.w);
                     const int nrow = slot * kNB + h_ml;
-                    const size_t o = (size_t)(nrow >> 3) * 32 + (size_t)h_cg * (p.NRr * 4) + (size_t)(nrow & 7) * 4;
+                    const size_t o = (size_t)(nrow >> 3) * 32 + (size_t)h_cg * (p.NRr * 4 + 4) + (size_t)(nrow & 7) * 4;
                     *reinterpret_cast<float4 *>(ring_hi + o) = hi;
                     *reinterpret_cast<float4 *>(ring_lo + o) = lo;
                     new_slots |= 1u << slot;                            // published below, behind one proxy fence
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         for (long long e = 0; e < n_epochs; ++e) drain(e);
     } else {
         // ------------------------------------ MMA issuers (converged warps, one elected lane each) ------------------------------------
-        const unsigned lbo_a = (unsigned)(2 * KP) * 16, lbo_b = (unsigned)p.NRr * 16;
+        const unsigned lbo_a = (unsigned)(2 * KP) * 16, lbo_b = (unsigned)p.NRr * 16 + 16;   // ring chunks carry a 16-byte pad
         const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
         const unsigned a_lo_word = ((lbo_a >> 4) << 16), b_lo_word = ((lbo_b >> 4) << 16);
         const unsigned ring16[3] = {smem_u32(ring_hi) >> 4, smem_u32(ring_hi) >> 4, smem_u32(ring_lo) >> 4};
