@@ -132,10 +132,11 @@ def test_batch_fit_custom_inhibition_range(golden):
     assert np.allclose(nmf.W, g['valid_range_W'], rtol=1e-8, atol=1e-12)
 
 
-@pytest.mark.parametrize('path', ['generic', 'tiled'])
+@pytest.mark.parametrize('path', ['generic', 'tiled', 'auto', 'tc'])
 def test_batch_fit_float32_100_iterations(path, golden):
     """north_star tolerance: energy trajectory within 1e-4 relative, W/H within 1e-3 max-relative after 100
-    iterations, against the reference numpy backend run in float32."""
+    iterations, against the reference numpy backend run in float32 - for every kernel family, the 3xTF32 tensor-core
+    H update and W gradient ('tc') included."""
     from tnmf_b200 import TransformInvariantNMF
     g = golden('ref_fit_2d')
     V32 = g['V'].astype(np.float32)
@@ -145,6 +146,9 @@ def test_batch_fit_float32_100_iterations(path, golden):
     nmf.fit(V32, n_iterations=100, sparsity_H=0.1,
             progress_callback=lambda m, i: traj.append(m._energy_function()) or True)
     assert nmf.W.dtype == np.float32 and nmf.H.dtype == np.float32
+    if path == 'tc':
+        fam = nmf._backend.kernel_families()
+        assert fam['update_h'] == 'tc' and fam['gradient_w'] == 'tc'
     assert np.allclose(traj, g['f32_E'], rtol=1e-4)
     assert np.abs(nmf.W - g['f32_W']).max() <= 1e-3 * np.abs(g['f32_W']).max()
     assert np.abs(nmf.H - g['f32_H']).max() <= 1e-3 * np.abs(g['f32_H']).max()
