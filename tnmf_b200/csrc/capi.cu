@@ -50,12 +50,15 @@ bool tc_worthwhile(const Geo &g) {
     return useful >= 0.5 && (long long)g.N * g.T[2] >= 128 && g.A[1] >= 3;
 }
 
-// The tensor-core W gradient stacks the expanded V and R rows into the 128 MMA lanes: 2 * roundup(C*A_x, 8) of them
-// carry taps.  'auto' takes it when that is at least half of the tile (TNMF_NO_TC_GRADW=1 keeps the FP32 kernel).
+// The tensor-core W gradient stacks the expanded V and R rows (of two consecutive source rows when the atom is narrow)
+// into the 128 MMA lanes: 2 * S * roundup(C*A_x, 8) of them carry taps.  'auto' takes it when that is at least half of
+// the tile (TNMF_NO_TC_GRADW=1 keeps the FP32 kernel).
 bool tc_gradw_worthwhile(const Geo &g) {
     if (getenv("TNMF_NO_TC") || getenv("TNMF_NO_TC_GRADW")) return false;
-    const int k = g.C * g.A[2], mp = (g.M + 15) / 16 * 16;
-    return 2 * k >= 64 && (double)g.M / mp >= 0.5 && (long long)g.N * g.T[2] >= 64 && g.A[1] >= 3;
+    const int kp = (g.C * g.A[2] + 7) / 8 * 8, mp = (g.M + 15) / 16 * 16;
+    const int stack = (4 * kp <= 128 && 16 * (g.A[1] + 1) <= 256) ? 2 : 1;
+    return 2 * stack * kp >= 64 && g.C * g.A[2] * 2 >= kp && (double)g.M / mp >= 0.5 && (long long)g.N * g.T[2] >= 64 &&
+           g.A[1] >= 3;
 }
 
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;

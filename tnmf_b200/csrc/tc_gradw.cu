@@ -21,7 +21,7 @@
 // following K chunk (finite values, their accumulator lanes are never read).
 //
 // Roles (448 threads): warps 0-7 workers (stage the new activation row into the ring, expand V and R), warps 8 and 9
-// issue the MMAs of the even / odd K steps (converged warps, one elected lane each), warps 10-13 drain the sets.  mbarriers: a_full/a_empty per operand stage, h_full/h_free per ring slot, set_done/set_free per set.
+// issue the MMAs of the two runs of the live-row window (converged warps, one elected lane each), warps 10-13 drain the sets.  mbarriers: a_full/a_empty per operand stage, h_full/h_free per ring slot, set_done/set_free per set.
 // Atoms in blocks of 16 (one launch per block).  Bound: tensor pipe at the TF32 rate / 3 with 2*KP/128 useful lanes.
 #include <cstdlib>
 #include "tc_common.cuh"
@@ -50,10 +50,12 @@ constexpr int kIssuers = TNMF_GW_ISSUERS;
 constexpr int kMaxStages = 4;
 constexpr int kMaxSmem = 226 * 1024;
 constexpr int kRawMax = 4;          // raw elements per worker and tensor pair: 2 * C * (64 + AX - 1) <= 1024
+constexpr int kRingMax = 18;        // ring slots (activation rows resident in shared memory)
 constexpr int kChunkMax = 8;        // 16-byte chunks of an operand stage per worker: 2 * KP * 16 <= 2048
 
 struct Plan {
     int KP, TXP, RW, raw_floats, nraw, nchunk;
+    int S, NP;                      // source rows stacked into one operand, operand planes = 2 S (row, V | R)
     int RS, NRr;                    // ring slots (AY + 1), ring rows (16 per slot)
     int ring_floats, stage_floats;  // floats of ONE of the hi / lo halves
     int tiles, rblocks, rows_per_block;
@@ -64,7 +66,7 @@ struct Plan {
 
 struct Args {
     const float *V, *R, *H;
-    float *partials;                // [grid][2][M*C*AY*AX]
+    float *partials;                // [grid][S][2][M*C*AY*AX]
     int m0;
 };
 
@@ -76,21 +78,25 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.TXP = g.TX + g.AX - 1;
     p.RW = kCT + g.AX - 1;
     p.raw_floats = round_up(g.C * p.RW + kCT + 8, 32);      // + zeros read by the padded k
-    p.nraw = ceil_div(2 * g.C * p.RW, kWorkers);
+    // narrow atoms (C*AX <= 32) leave most of the 128 MMA lanes empty: stack two consecutive source rows, whose
+    // live-row windows differ by one activation row, into the same operand
+    p.S = (4 * p.KP <= 128 && kNB * (g.AY + 1) <= 256) ? 2 : 1;
+    p.NP = 2 * p.S;
+    p.nraw = ceil_div(p.NP * g.C * p.RW, kWorkers);
     if (p.nraw > kRawMax) return false;
-    p.nchunk = ceil_div(2 * p.KP * (kCT / 4), kWorkers);
+    p.nchunk = ceil_div(p.NP * p.KP * (kCT / 4), kWorkers);
     if (p.nchunk > kChunkMax) return false;
-    p.stage_floats = 2 * p.KP * kCT;
+    p.stage_floats = p.NP * p.KP * kCT;
     // ring slots: AY + 1 at least; more (up to 16) while two operand stages still fit - a longer ring splits fewer
     // live-row windows at its wrap-around, and every split costs an extra MMA on the 46-clk issue floor
     size_t fixed = 0;
-    for (p.RS = 16; p.RS >= g.AY + 1; --p.RS) {
+    for (p.RS = kRingMax; p.RS >= g.AY + p.S; --p.RS) {
         p.NRr = p.RS * kNB;
         p.ring_floats = (p.NRr * 4 + 4) * (kCT / 4);        // K-chunk stride padded by 16 bytes: conflict-free row staging
-        fixed = (size_t)2 * p.ring_floats * 4 + (size_t)8 * p.raw_floats * 4 + 4096;   // + over-read pad
+        fixed = (size_t)2 * p.ring_floats * 4 + (size_t)4 * p.NP * p.raw_floats * 4 + 4096;   // + over-read pad
         if (fixed + 2 * (size_t)2 * p.stage_floats * 4 <= (size_t)kMaxSmem) break;
     }
-    if (p.RS < g.AY + 1) return false;
+    if (p.RS < g.AY + p.S) return false;
     p.n_stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)2 * p.stage_floats * 4));
     if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
     p.smem = fixed + (size_t)p.n_stages * 2 * p.stage_floats * 4;
@@ -137,26 +143,27 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, const Plan p, const Args a) {
     extern __shared__ __align__(128) float smem[];
-    __shared__ __align__(8) unsigned long long a_full[kMaxStages], a_empty[kMaxStages], h_full[16], h_free[16], set_done[2],
+    __shared__ __align__(8) unsigned long long a_full[kMaxStages], a_empty[kMaxStages], h_full[kRingMax], h_free[kRingMax], set_done[2],
         set_free[2];
     __shared__ unsigned tmem_base_s;
     __shared__ __align__(16) int koff[64];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int KP = p.KP, AY = g.AY, AX = g.AX, C = g.C, RS = p.RS, RW = p.RW;
+    const int KP = p.KP, AY = g.AY, AX = g.AX, C = g.C, RS = p.RS, RW = p.RW, S = p.S, NP = p.NP;
     float *ring_hi = smem, *ring_lo = smem + p.ring_floats;
-    float *raw = ring_lo + p.ring_floats;                       // [2 buffers][hi, lo][V, R][raw_floats]
-    float *stages = raw + 8 * p.raw_floats;                     // [stage][hi, lo][stage_floats]
+    float *raw = ring_lo + p.ring_floats;                       // [2 buffers][hi, lo][plane][raw_floats]
+    float *stages = raw + 4 * NP * p.raw_floats;                     // [stage][hi, lo][stage_floats]
 
     if (tid == 0) {
         for (int s = 0; s < p.n_stages; ++s) { mbar_init(&a_full[s], kWorkers); mbar_init(&a_empty[s], kIssuers); }
-        for (int s = 0; s < 16; ++s) { mbar_init(&h_full[s], kWorkers); mbar_init(&h_free[s], kIssuers); }
+        for (int s = 0; s < kRingMax; ++s) { mbar_init(&h_full[s], kWorkers); mbar_init(&h_free[s], kIssuers); }
         for (int s = 0; s < 2; ++s) { mbar_init(&set_done[s], kIssuers); mbar_init(&set_free[s], 128); }
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(&tmem_base_s, 512);
     if (tid < KP) koff[tid] = tid < C * AX ? (tid / AX) * RW + (tid % AX) : C * RW;
     // zeros behind every raw array (read through the padded k) - written once
-    for (int idx = tid; idx < 8 * (kCT + 8); idx += kThreads) raw[(idx / (kCT + 8)) * p.raw_floats + C * RW + (idx % (kCT + 8))] = 0.f;
+    for (int idx = tid; idx < 4 * NP * (kCT + 8); idx += kThreads)
+        raw[(idx / (kCT + 8)) * p.raw_floats + C * RW + (idx % (kCT + 8))] = 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -181,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         prof_total = -clock64();
 #endif
         const long long plane = (long long)g.DY * g.DX;
-        const int raw_count = 2 * C * RW;
+        const int raw_count = NP * C * RW;
         // operand chunks of this thread: q = tid + 256 e -> (column group cg, operand row); fixed for the kernel
         int c_src[kChunkMax], c_dst[kChunkMax];
 #pragma unroll
@@ -189,11 +196,11 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
             const int q = tid + kWorkers * e;
             c_src[e] = -1;
             c_dst[e] = 0;
-            if (e < p.nchunk && q < 2 * KP * (kCT / 4)) {
-                const int cg = q / (2 * KP), row = q - cg * (2 * KP);
-                const int X = row >= KP ? 1 : 0, k = row - X * KP;
-                c_src[e] = X * p.raw_floats + koff[k] + 4 * cg;
-                c_dst[e] = (row >> 3) * 32 + cg * (2 * KP * 4) + (row & 7) * 4;
+            if (e < p.nchunk && q < NP * KP * (kCT / 4)) {
+                const int cg = q / (NP * KP), row = q - cg * (NP * KP);
+                const int P = row / KP, k = row - P * KP;            // plane = (source row s, V | R)
+                c_src[e] = P * p.raw_floats + koff[k] + 4 * cg;
+                c_dst[e] = (row >> 3) * 32 + cg * (NP * KP * 4) + (row & 7) * 4;
             }
         }
         // activation chunk of this thread: atom ml, columns 4 cg .. 4 cg + 3 of the tile
@@ -208,7 +215,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                 roff[e] = -1;
                 const int q = tid + kWorkers * e;
                 if (e < p.nraw && q < raw_count) {
-                    const int X = q >= C * RW ? 1 : 0, qq = q - X * C * RW;
+                    const int qq = q % (C * RW);
                     const int c = qq / RW;
                     const long long J = (long long)w.tile * kCT + (qq - c * RW);
                     const int n = (int)(J / p.TXP);
@@ -228,11 +235,12 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
             }
             float rv[kRawMax];
             auto load_raw = [&](int r) {
-                const long long row = (long long)r * g.DX;
 #pragma unroll
                 for (int e = 0; e < kRawMax; ++e) {
-                    const float *src = (tid + kWorkers * e >= C * RW) ? a.R : a.V;
-                    rv[e] = roff[e] >= 0 ? __ldg(src + row + roff[e]) : 0.f;
+                    const int P = (tid + kWorkers * e) / (C * RW);       // plane -> source row r + P / 2, tensor P & 1
+                    const int rr = r + (P >> 1);
+                    const float *src = (P & 1) ? a.R : a.V;
+                    rv[e] = (roff[e] >= 0 && rr <= w.r_hi) ? __ldg(src + (long long)rr * g.DX + roff[e]) : 0.f;
                 }
             };
             // activation row fetch, issued one source row ahead of its use (interior rows bring exactly one new row)
@@ -248,9 +256,9 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
             int hv_row = -1;
             int next_new = w.ty0;
             load_raw(w.r_lo);
-            for (int r = w.r_lo; r <= w.r_hi; ++r) {
-                // ---- activation rows that enter the window with this source row ----
-                const int t_b = min(w.ty1 - 1, r + g.offy);
+            for (int r = w.r_lo; r <= w.r_hi; r += S) {
+                // ---- activation rows that enter the window with this group of source rows ----
+                const int t_b = min(w.ty1 - 1, min(r + S - 1, w.r_hi) + g.offy);
                 unsigned new_slots = 0;
                 for (; next_new <= t_b; ++next_new) {
                     const long long gi = g_base + (next_new - w.ty0);
@@ -276,19 +284,19 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                 const long long t_r = clock64();
 #endif
                 // ---- expanded V and R rows ----
-                float *raw_hi = raw + (size_t)buf * 4 * p.raw_floats, *raw_lo = raw_hi + 2 * p.raw_floats;
+                float *raw_hi = raw + (size_t)buf * 2 * NP * p.raw_floats, *raw_lo = raw_hi + NP * p.raw_floats;
 #pragma unroll
                 for (int e = 0; e < kRawMax; ++e) {
                     const int q = tid + kWorkers * e;
                     if (e < p.nraw && q < raw_count) {
                         float hi, lo;
                         split_tf32(rv[e], hi, lo);
-                        const int X = q >= C * RW ? 1 : 0;
-                        raw_hi[X * p.raw_floats + (q - X * C * RW)] = hi;
-                        raw_lo[X * p.raw_floats + (q - X * C * RW)] = lo;
+                        const int P = q / (C * RW);
+                        raw_hi[P * p.raw_floats + (q - P * C * RW)] = hi;
+                        raw_lo[P * p.raw_floats + (q - P * C * RW)] = lo;
                     }
                 }
-                if (r < w.r_hi) load_raw(r + 1);                      // in flight while this row is expanded
+                if (r + S <= w.r_hi) load_raw(r + S);                 // in flight while this group is expanded
                 if (next_new < w.ty1) { hv_next = load_h(next_new); hv_row = next_new; }
 #ifdef TNMF_TC_PROFILE
                 prof_rawp += clock64() - t_r;
@@ -334,18 +342,19 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
             mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100);
             tc_fence_after();
             const int l = (warp & 3) * 32 + lane;
-            const int X = l >= KP ? 1 : 0, k = l - X * KP;
-            const bool live = l < 2 * KP && k < C * AX;
+            const int P = l / KP, k = l - P * KP;                       // plane = (stacked row s, V | R)
+            const int sr = P >> 1, X = P & 1;
+            const bool live = P < NP && k < C * AX;
             const int c = live ? k / AX : 0, ax = live ? k - c * AX : 0;
-            float *slice = a.partials + (long long)blockIdx.x * 2 * count + (long long)X * count;
+            float *slice = a.partials + ((long long)blockIdx.x * S + sr) * 2 * count + (long long)X * count;
             const unsigned tbase = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(set * 256);
-            for (int j = 0; j < AY; ++j) {
+            for (int j = 0; j < AY + S - 1; ++j) {
                 float v[16];
                 tmem_ld16(tbase + (unsigned)(j * kNB), v);
                 tmem_ld_wait();
                 tmem_st16_zero(tbase + (unsigned)(j * kNB));
-                const int ay = AY - 1 - j;
-                if (live) {
+                const int ay = AY - 1 - j + sr;                         // stacked row s sees the window one row later
+                if (live && ay >= 0 && ay < AY) {
                     // all 16 running sums are fetched before the first store (stores would otherwise order the loads)
                     float *dst0 = slice + (((long long)a.m0 * C + c) * AY + ay) * AX + ax;
                     const long long mstride = (long long)C * AY * AX;
@@ -365,19 +374,19 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         };
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
-            rows_done += w.r_hi - w.r_lo + 1;
+            rows_done += (w.r_hi - w.r_lo + S) / S;                 // groups of S source rows
         }
         const long long n_epochs = (rows_done + kEpoch - 1) / kEpoch;
         for (long long e = 0; e < n_epochs; ++e) drain(e);
     } else {
         // ------------------------------------ MMA issuers (converged warps, one elected lane each) ------------------------------------
-        const unsigned lbo_a = (unsigned)(2 * KP) * 16, lbo_b = (unsigned)p.NRr * 16 + 16;   // ring chunks carry a 16-byte pad
+        const unsigned lbo_a = (unsigned)(NP * KP) * 16, lbo_b = (unsigned)p.NRr * 16 + 16;   // ring chunks carry a 16-byte pad
         const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
         const unsigned a_lo_word = ((lbo_a >> 4) << 16), b_lo_word = ((lbo_b >> 4) << 16);
         const unsigned ring16[3] = {smem_u32(ring_hi) >> 4, smem_u32(ring_hi) >> 4, smem_u32(ring_lo) >> 4};
         const unsigned stage_addr0 = smem_u32(stages);
         const unsigned a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
-        const int x = warp - 8;                 // warp 8 issues the even K steps, warp 9 the odd ones
+        const int x = warp - 8;                 // warp 8 issues the first run of the live-row window, warp 9 the second
         int st = 0;
         unsigned ph = 0;
         long long g_base = 0, rows_done = 0;
@@ -388,15 +397,16 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             int next_new = w.ty0, next_out = w.ty0;
-            for (int r = w.r_lo; r <= w.r_hi; ++r) {
+            for (int r = w.r_lo; r <= w.r_hi; r += S) {
+                const int r_end = min(r + S - 1, w.r_hi);           // last source row of the group
                 const long long epoch = rows_done / kEpoch;
                 if (rows_done % kEpoch == 0 && epoch >= 2) {
                     TC_PROF_WAIT(setfree, mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1)));
                     tc_fence_after();
                 }
                 const unsigned tset = tmem_base + (unsigned)((epoch & 1) * 256);
-                const int ay_lo = max(0, r + g.offy - (w.ty1 - 1)), ay_hi = min(AY - 1, r + g.offy - w.ty0);
-                const int t_a = r + g.offy - ay_hi, t_b = r + g.offy - ay_lo;
+                const int ay_hi = min(AY - 1, r + g.offy - w.ty0);
+                const int t_a = r + g.offy - ay_hi, t_b = min(w.ty1 - 1, r_end + g.offy);
                 const int j0 = r + g.offy - AY + 1;                 // activation row of accumulator column block 0
                 for (; next_new <= t_b; ++next_new) {
                     const long long gi = g_base + (next_new - w.ty0);
@@ -404,40 +414,45 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                 }
                 TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
                 tc_fence_after();
-                // the window [t_a, t_b] in ring order: at most two runs of slots
-                unsigned o_col[2], o_idesc[2], o_b16[2];
-                int n_ops = 0;
+                // The window [t_a, t_b] is cut into kIssuers runs of ring slots, one per issuing warp: at the ring's
+                // wrap-around when it wraps, else in the middle.  Each warp issues ALL K steps of its run, so the runs
+                // accumulate into disjoint TMEM columns in a fixed order - the result does not depend on how the two
+                // warps interleave in the tensor pipe (splitting the K steps between the warps did: bitwise
+                // run-to-run differences, caught by the graph-vs-eager test).
+                unsigned o_col = 0, o_idesc = 0, o_b16 = 0;
+                bool have = false;
                 {
                     const int cnt = t_b - t_a + 1;
-                    const int s = (int)((g_base + (t_a - w.ty0)) % RS);
-                    const int first = min(cnt, RS - s);
-                    o_col[0] = (unsigned)((t_a - j0) * kNB); o_idesc[0] = idesc_tf32(128, kNB * first);
-                    o_b16[0] = (unsigned)s * 16u; n_ops = 1;
-                    if (cnt > first) {
-                        o_col[1] = (unsigned)((t_a - j0 + first) * kNB); o_idesc[1] = idesc_tf32(128, kNB * (cnt - first));
-                        o_b16[1] = 0u; n_ops = 2;
+                    const int s0 = (int)((g_base + (t_a - w.ty0)) % RS);
+                    int first = min(cnt, RS - s0);                      // slots before the wrap-around
+                    if (kIssuers > 1 && first == cnt && cnt > 1) first = (cnt + 1) / 2;
+                    if (kIssuers == 1 || x == 0) {
+                        have = true;
+                        o_col = (unsigned)((t_a - j0) * kNB); o_idesc = idesc_tf32(128, kNB * first); o_b16 = (unsigned)s0 * 16u;
+                    } else if (x == 1 && cnt > first) {
+                        have = true;
+                        o_col = (unsigned)((t_a - j0 + first) * kNB); o_idesc = idesc_tf32(128, kNB * (cnt - first));
+                        o_b16 = (unsigned)((s0 + first) % RS) * 16u;
                     }
                 }
                 const unsigned a_hi16 = (stage_addr0 + (unsigned)st * 2u * (unsigned)p.stage_floats * 4u) >> 4;
                 const unsigned a_addr16[3] = {a_hi16, a_hi16 + (((unsigned)p.stage_floats * 4u) >> 4), a_hi16};
-                for (int ks = x; ks < kCT / 8; ks += kIssuers) {
+                if (have) {
+                    for (int ks = 0; ks < kCT / 8; ++ks) {
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        const unsigned long long da =
-                            ((unsigned long long)desc_hi << 32) | (a_lo_word | (a_addr16[t] + ks * a_step16));
-                        const unsigned b16 = ring16[t] + ks * b_step16;
-                        mma_tf32_elect(tset + o_col[0], da,
-                                       ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[0])), o_idesc[0], 1u);
-                        if (n_ops > 1)
-                            mma_tf32_elect(tset + o_col[1], da,
-                                           ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[1])), o_idesc[1],
-                                           1u);
+                        for (int t = 0; t < 3; ++t) {
+                            const unsigned long long da =
+                                ((unsigned long long)desc_hi << 32) | (a_lo_word | (a_addr16[t] + ks * a_step16));
+                            const unsigned b16 = ring16[t] + ks * b_step16;
+                            mma_tf32_elect(tset + o_col, da,
+                                           ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16)), o_idesc, 1u);
+                        }
                     }
                 }
                 mma_commit_elect(&a_empty[st]);
                 if (++st == p.n_stages) { st = 0; ph ^= 1u; }
                 // activation rows that leave the window: their slots may be overwritten once these MMAs are done
-                for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r; ++next_out)
+                for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r_end; ++next_out)
                     mma_commit_elect(&h_free[(g_base + (next_out - w.ty0)) % RS]);
                 if (++rows_done % kEpoch == 0) mma_commit_elect(&set_done[epoch & 1]);
             }
@@ -473,7 +488,7 @@ bool tc_gradw_supported(const Geo &g, int dtype) {
 size_t tc_gradw_workspace_bytes(const Geo &g) {
     tc::gw::Plan p;
     if (!tc::gw::make_plan(tiled::make_geo2(g), p)) return 0;
-    return (size_t)p.grid * 2 * (size_t)g.M * g.C * g.A[1] * g.A[2] * sizeof(float);
+    return (size_t)p.grid * p.S * 2 * (size_t)g.M * g.C * g.A[1] * g.A[2] * sizeof(float);
 }
 
 int tc_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
@@ -493,7 +508,7 @@ int tc_gradient_w(const Geo &g, const float *V, const float *R, const float *H, 
         tc::gw::gradw_tc_kernel<<<(unsigned)p.grid, tc::gw::kThreads, p.smem, st>>>(q, p, a);
         TNMF_CHECK_LAUNCH();
     }
-    return finish_gradient_w<float>((const float *)workspace, p.grid, count, neg, pos, st);
+    return finish_gradient_w<float>((const float *)workspace, p.grid * p.S, count, neg, pos, st);
 }
 
 int tc_gradw_launches(const Geo &g) { return tiled::ceil_div(g.M, tc::gw::kNB) + 1; }
