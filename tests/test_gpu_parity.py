@@ -424,6 +424,38 @@ def test_tc_gradient_w_vs_oracle(case, mode):
     _close(Wd, nmf.W, 5e-5)
 
 
+@pytest.mark.parametrize('seed', range(10))
+def test_tc_kernels_vs_generic_on_random_shapes(seed):
+    """Randomly drawn supported shapes (ragged tiles, rows far beyond one trip round the TMEM / activation rings, atom
+    counts off the blocks of 16, both modes): the tensor-core kernels against the one-thread-per-output generic kernels
+    on the same device tensors."""
+    rng = np.random.default_rng(9000 + seed)
+    C = int(rng.integers(1, 4))
+    AX = int(rng.integers(1, 64 // C // 2 + 1))
+    AY = int(rng.integers(1, 16))
+    M = int(rng.integers(1, 40))
+    N = int(rng.integers(1, 6))
+    D = (int(rng.integers(AY, AY + 90)), int(rng.integers(AX, AX + 150)))
+    mode = 'valid' if seed % 2 == 0 else 'full'
+    A = (AY, AX)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    out = {}
+    for path in ('generic', 'tc'):
+        be, Wd, Hd = _backend(V, W, H, mode, path)
+        be.reconstruct(Wd, Hd)
+        if path == 'tc':
+            fam = be.kernel_families()
+            assert fam['update_h'] == 'tc' and fam['gradient_w'] == 'tc', (fam, C, A, M)
+        nh, ph = be.reconstruction_gradient_H(V, Wd, Hd)
+        nw, pw = be.reconstruction_gradient_W(V, Wd, Hd)
+        be.update_H(V, Wd, Hd, slice(None), 0.05)
+        out[path] = [t.cpu().numpy().astype(np.float64) for t in (nh, ph, nw, pw, Hd)]
+    for got, ref, tol in zip(out['tc'], out['generic'], (2e-5, 2e-5, 2e-5, 2e-5, 1e-4)):
+        _close(got, ref, tol)
+
+
 @pytest.mark.parametrize('kw', [dict(), dict(sparsity_H=0.05, inhibition_strength=0.1, cross_atom_inhibition_strength=0.05),
                                 dict(update_W=False), dict(update_H=False)])
 def test_cuda_graph_replay_equals_eager_launches(kw):

@@ -79,24 +79,28 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.RW = kCT + g.AX - 1;
     p.raw_floats = round_up(g.C * p.RW + kCT + 8, 32);      // + zeros read by the padded k
     // narrow atoms (C*AX <= 32) leave most of the 128 MMA lanes empty: stack two consecutive source rows, whose
-    // live-row windows differ by one activation row, into the same operand
-    p.S = (4 * p.KP <= 128 && kNB * (g.AY + 1) <= 256) ? 2 : 1;
-    p.NP = 2 * p.S;
-    p.nraw = ceil_div(p.NP * g.C * p.RW, kWorkers);
-    if (p.nraw > kRawMax) return false;
-    p.nchunk = ceil_div(p.NP * p.KP * (kCT / 4), kWorkers);
-    if (p.nchunk > kChunkMax) return false;
-    p.stage_floats = p.NP * p.KP * kCT;
-    // ring slots: AY + 1 at least; more (up to 16) while two operand stages still fit - a longer ring splits fewer
-    // live-row windows at its wrap-around, and every split costs an extra MMA on the 46-clk issue floor
+    // live-row windows differ by one activation row, into the same operand - when the lanes, the accumulator columns,
+    // the per-thread work lists and shared memory allow it
     size_t fixed = 0;
-    for (p.RS = kRingMax; p.RS >= g.AY + p.S; --p.RS) {
-        p.NRr = p.RS * kNB;
-        p.ring_floats = (p.NRr * 4 + 4) * (kCT / 4);        // K-chunk stride padded by 16 bytes: conflict-free row staging
-        fixed = (size_t)2 * p.ring_floats * 4 + (size_t)4 * p.NP * p.raw_floats * 4 + 4096;   // + over-read pad
-        if (fixed + 2 * (size_t)2 * p.stage_floats * 4 <= (size_t)kMaxSmem) break;
+    bool ok = false;
+    for (p.S = 2; p.S >= 1 && !ok; --p.S) {
+        if (p.S * 2 * p.KP > 128 || kNB * (g.AY + p.S - 1) > 256) continue;
+        p.NP = 2 * p.S;
+        p.nraw = ceil_div(p.NP * g.C * p.RW, kWorkers);
+        p.nchunk = ceil_div(p.NP * p.KP * (kCT / 4), kWorkers);
+        if (p.nraw > kRawMax || p.nchunk > kChunkMax) continue;
+        p.stage_floats = p.NP * p.KP * kCT;
+        // ring slots: AY + S at least; more while two operand stages still fit - a longer ring splits fewer live-row
+        // windows at its wrap-around, and every split costs an extra MMA on the 46-clk issue floor
+        for (p.RS = kRingMax; p.RS >= g.AY + p.S; --p.RS) {
+            p.NRr = p.RS * kNB;
+            p.ring_floats = (p.NRr * 4 + 4) * (kCT / 4);    // K-chunk stride padded by 16 bytes: conflict-free row staging
+            fixed = (size_t)2 * p.ring_floats * 4 + (size_t)4 * p.NP * p.raw_floats * 4 + 4096;   // + over-read pad
+            if (fixed + 2 * (size_t)2 * p.stage_floats * 4 <= (size_t)kMaxSmem) { ok = true; break; }
+        }
+        if (ok) break;
     }
-    if (p.RS < g.AY + p.S) return false;
+    if (!ok) return false;
     p.n_stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)2 * p.stage_floats * 4));
     if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
     p.smem = fixed + (size_t)p.n_stages * 2 * p.stage_floats * 4;
