@@ -19,7 +19,9 @@ METRICS = [
     ('launch__registers_per_thread', 'regs/thread'),
     ('launch__shared_mem_per_block_dynamic', 'dyn smem/block'),
     ('sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'FMA pipe active %'),
-    ('sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'tensor pipe active % (elapsed)'),
+    ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor pipe active %'),
+    ('sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed', 'TF32 tcgen05 ops, % of peak (elapsed)'),
+    ('sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor memory (TMEM) active %'),
     ('sm__inst_executed_pipe_tc.sum', 'tcgen05 MMA instructions'),
     ('l1tex__data_pipe_tc_wavefronts_mem_shared.sum', 'smem wavefronts read by the tensor core'),
     ('l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smem wavefronts LSU (ld + st)'),
