@@ -456,6 +456,55 @@ def test_tc_kernels_vs_generic_on_random_shapes(seed):
         _close(got, ref, tol)
 
 
+@pytest.mark.parametrize('path', ['tc', 'auto'])
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+def test_no_out_of_bounds_access_nan_guards(mode, path):
+    """V and H live inside larger buffers whose surroundings are NaN (compute-sanitizer is not available on the GPU
+    pool): an out-of-bounds read poisons the results, an out-of-bounds write destroys a guard.  Shapes chosen so that
+    tiles are ragged in every direction and the last column tile is mostly empty."""
+    N, C, M, D, A = 3, 3, 16, (37, 70), (11, 11)
+    rng = np.random.default_rng(31)
+    T = orc.transform_shape(mode, D, A)
+    pitch = (T[1] + 3) // 4 * 4
+    guard = 4096
+    dev = torch.device('cuda')
+    Vbig = torch.full((guard + N * C * D[0] * D[1] + guard,), float('nan'), device=dev)
+    V = Vbig[guard:guard + N * C * D[0] * D[1]].view(N, C, *D)
+    V.copy_(torch.from_numpy(rng.random((N, C) + D).astype(np.float32)))
+    Hbig = torch.full((guard + N * M * T[0] * pitch + guard,), float('nan'), device=dev)
+    Hpad = Hbig[guard:guard + N * M * T[0] * pitch].view(N, M, T[0], pitch)
+    H = Hpad[..., :T[1]]
+    H.copy_(torch.from_numpy(rng.random((N, M) + T).astype(np.float32)))
+    W = rng.random((M, C) + A).astype(np.float32)
+    from tnmf_b200 import B200_Backend
+    be = B200_Backend(reconstruction_mode=mode, kernel_path=path)
+    state = np.random.get_state()
+    Wd, _ = be.initialize(V, A, M, None, (-2, -1))
+    np.random.set_state(state)
+    Wd.copy_(torch.from_numpy(W))
+    V64, W64 = V.cpu().numpy().astype(np.float64), W.astype(np.float64)
+    H64 = H.cpu().numpy().astype(np.float64)
+    neg, pos = be.reconstruction_gradient_H(V, Wd, H)
+    rn, rp = orc.reconstruction_gradient_H(V64, W64, H64, mode)
+    _close(neg, rn, 2e-5)
+    _close(pos, rp, 2e-5)
+    neg, pos = be.reconstruction_gradient_W(V, Wd, H)
+    rn, rp = orc.reconstruction_gradient_W(V64, W64, H64, mode)
+    _close(neg, rn, 2e-5)
+    _close(pos, rp, 2e-5)
+    assert np.isclose(be.reconstruction_energy(V, Wd, H), orc.reconstruction_energy(V64, W64, H64, mode), rtol=2e-5)
+    be.update_H(V, Wd, H)
+    nmf = orc.OracleNMF(M, A, reconstruction_mode=mode)
+    nmf.V, nmf.W, nmf.H = V64, W64.copy(), H64.copy()
+    nmf.update_H(slice(None))
+    _close(H, nmf.H, 1e-4)
+    torch.cuda.synchronize()
+    assert bool(torch.isnan(Hbig[:guard]).all()) and bool(torch.isnan(Hbig[-guard:]).all())
+    assert bool(torch.isnan(Vbig[:guard]).all()) and bool(torch.isnan(Vbig[-guard:]).all())
+    if pitch > T[1]:
+        assert bool(torch.isnan(Hpad[..., T[1]:]).all())           # the pitch padding of every row is never written
+
+
 @pytest.mark.parametrize('kw', [dict(), dict(sparsity_H=0.05, inhibition_strength=0.1, cross_atom_inhibition_strength=0.05),
                                 dict(update_W=False), dict(update_H=False)])
 def test_cuda_graph_replay_equals_eager_launches(kw):
