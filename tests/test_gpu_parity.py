@@ -424,6 +424,28 @@ def test_tc_gradient_w_vs_oracle(case, mode):
     _close(Wd, nmf.W, 5e-5)
 
 
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+@pytest.mark.parametrize('case', range(len(TC_CASES)))
+def test_tc_reconstruct_vs_oracle(case, mode):
+    """Tensor-core reconstruction (input-stationary, shifted-operand MMAs, register ring of output rows) and its fused
+    energy against the oracle, plus the strided single-atom view of partial_reconstruct (which the FP32 kernels serve)."""
+    N, C, M, D, A = TC_CASES[case]
+    rng = np.random.default_rng(500 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    R = be.reconstruct(Wd, Hd)
+    assert be.kernel_families()['reconstruct'] == 'tc'
+    ref = orc.reconstruct(W64, H64, mode)
+    _close(R, ref, 2e-5)
+    assert np.isclose(be.reconstruction_energy(V, Wd, Hd), orc.reconstruction_energy(V64, W64, H64, mode), rtol=2e-5)
+    if N > 2:                                   # a slice of the samples (minibatch call)
+        _close(be.reconstruct(Wd, Hd[1:N - 1]), ref[1:N - 1], 2e-5)
+    _close(be.partial_reconstruct(Wd, Hd, M - 1), orc.reconstruct(W64[M - 1:], H64[:, M - 1:], mode), 2e-5)
+
+
 @pytest.mark.parametrize('seed', range(10))
 def test_tc_kernels_vs_generic_on_random_shapes(seed):
     """Randomly drawn supported shapes (ragged tiles, rows far beyond one trip round the TMEM / activation rings, atom
@@ -444,15 +466,15 @@ def test_tc_kernels_vs_generic_on_random_shapes(seed):
     out = {}
     for path in ('generic', 'tc'):
         be, Wd, Hd = _backend(V, W, H, mode, path)
-        be.reconstruct(Wd, Hd)
+        R = be.reconstruct(Wd, Hd)
         if path == 'tc':
             fam = be.kernel_families()
             assert fam['update_h'] == 'tc' and fam['gradient_w'] == 'tc', (fam, C, A, M)
         nh, ph = be.reconstruction_gradient_H(V, Wd, Hd)
         nw, pw = be.reconstruction_gradient_W(V, Wd, Hd)
         be.update_H(V, Wd, Hd, slice(None), 0.05)
-        out[path] = [t.cpu().numpy().astype(np.float64) for t in (nh, ph, nw, pw, Hd)]
-    for got, ref, tol in zip(out['tc'], out['generic'], (2e-5, 2e-5, 2e-5, 2e-5, 1e-4)):
+        out[path] = [t.cpu().numpy().astype(np.float64) for t in (nh, ph, nw, pw, Hd, R)]
+    for got, ref, tol in zip(out['tc'], out['generic'], (2e-5, 2e-5, 2e-5, 2e-5, 1e-4, 2e-5)):
         _close(got, ref, tol)
 
 

@@ -341,7 +341,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         if op == _lib.OP_GRADIENT_W:
             return (p.n_atoms + 15) // 16 + 1 if fam == _lib.PATHS['tc'] else 2
         if fam == _lib.PATHS['tc']:
-            return (p.n_atoms + 15) // 16        # one launch per block of 16 atoms
+            return 1 if op == _lib.OP_RECONSTRUCT else (p.n_atoms + 15) // 16    # H update: one launch per 16 atoms
         return 2 if fam == _lib.PATHS['tma'] else 1
 
     def reconstruction_gradient_H(self, V, W, H, s: slice = sliceNone):

@@ -50,6 +50,14 @@ bool tc_worthwhile(const Geo &g) {
     return useful >= 0.5 && (long long)g.N * g.T[2] >= 128 && g.A[1] >= 3;
 }
 
+// The tensor-core reconstruction has N = roundup(A_y * C, 16) <= 64: every MMA sits on the per-instruction floor, so it
+// pays when many (atom row, channel) pairs share one MMA and the atoms fill the K steps (TNMF_NO_TC_RECON=1 keeps FP32).
+bool tc_recon_worthwhile(const Geo &g) {
+    if (getenv("TNMF_NO_TC") || getenv("TNMF_NO_TC_RECON")) return false;
+    const int km = (g.M + 7) / 8 * 8;
+    return g.A[1] * g.C >= 24 && (double)g.M / km >= 0.75 && (long long)g.N * g.D[2] >= 128;
+}
+
 // The tensor-core W gradient stacks the expanded V and R rows (of two consecutive source rows when the atom is narrow)
 // into the 128 MMA lanes: 2 * S * roundup(C*A_x, 8) of them carry taps.  'auto' takes it when that is at least half of
 // the tile (TNMF_NO_TC_GRADW=1 keeps the FP32 kernel).
@@ -68,6 +76,9 @@ int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
     if (p->path == TNMF_PATH_GENERIC) return TNMF_PATH_GENERIC;
     if (op == TNMF_OP_GRADIENT_H && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_worthwhile(g))) &&
         tc_hupd_supported(g, p->dtype))
+        return TNMF_PATH_TC;
+    if (op == TNMF_OP_RECONSTRUCT && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_worthwhile(g))) &&
+        tc_recon_supported(g, p->dtype))
         return TNMF_PATH_TC;
     if (op == TNMF_OP_GRADIENT_W && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_gradw_worthwhile(g))) &&
         tc_gradw_supported(g, p->dtype))
@@ -167,6 +178,8 @@ int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *
     cudaStream_t st = (cudaStream_t)stream;
     int family = choose_family(p, g, TNMF_OP_RECONSTRUCT, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TC)
+        return tc_reconstruct(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
     if (family == TNMF_PATH_TMA && (!aligned16(H) || !workspace)) {
         if (p->path == TNMF_PATH_TMA) return workspace ? TNMF_EUNSUPPORTED : TNMF_EWORKSPACE;
         family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
@@ -205,7 +218,9 @@ int tnmf_reconstruct_energy(const tnmf_problem *p, const void *V, const void *W,
         family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
     }
     const bool tiled = family == TNMF_PATH_TILED;
-    if (family == TNMF_PATH_TMA) {
+    if (family == TNMF_PATH_TC) {
+        s = tc_reconstruct(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials, st);
+    } else if (family == TNMF_PATH_TMA) {
         partials = tma_energy_partials(g, workspace);
         s = tma_reconstruct(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials,
                             workspace, workspace_bytes, st);

@@ -98,6 +98,12 @@ int tc_gradw_launches(const Geo &g);
 int tc_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
                   size_t workspace_bytes, cudaStream_t st);
 
+// ---- implemented in tc_recon.cu (tcgen05 3xTF32) ------------------------------------------------------------
+bool tc_recon_supported(const Geo &g, int dtype);
+int tc_recon_partials(const Geo &g);
+int tc_reconstruct(const Geo &g, const float *W, const float *H, float *R, const float *V, double *energy_partials,
+                   int *n_partials, cudaStream_t st);
+
 // ---- implemented in elementwise.cu ----------------------------------------------------------------------
 int finish_energy(const double *partials, int n, double *energy, cudaStream_t st);
 template <typename T> int finish_gradient_w(const T *partials, int n_partials, long long count, T *neg, T *pos,
