@@ -79,11 +79,15 @@ def test_tiled_path_selection(lib, monkeypatch):
     # allow it (H rows of 266 floats are not 16-byte multiples)
     fam = lambda p, op: lib.tnmf_kernel_family(ctypes.byref(p), op)
     assert fam(f32_2d, _lib.OP_GRADIENT_H) == _lib.PATHS['tc']
+    assert fam(f32_2d, _lib.OP_RECONSTRUCT) == _lib.PATHS['tc']
+    monkeypatch.setenv('TNMF_NO_TC_RECON', '1')
     assert fam(f32_2d, _lib.OP_RECONSTRUCT) == _lib.PATHS['tiled']
     padded = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, h_pitch=268)
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma'], _lib.PATHS['tc'], _lib.PATHS['tc']]
+    monkeypatch.delenv('TNMF_NO_TC_RECON')
+    assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tc']] * 3
     monkeypatch.setenv('TNMF_NO_TC_GRADW', '1')
-    assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma'], _lib.PATHS['tc'], _lib.PATHS['tma']]
+    assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tc'], _lib.PATHS['tc'], _lib.PATHS['tma']]
     monkeypatch.delenv('TNMF_NO_TC_GRADW')
     monkeypatch.setenv('TNMF_NO_TC', '1')
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3

@@ -15,10 +15,11 @@
 //   * the epilogue thread of a column keeps the AY output rows in flight in REGISTERS: it adds Q[.., (ay, c)] to the
 //     partial sum of row y = ty - offy + ay, emits row ty - offy (complete) and shifts the ring by one row.
 // 3xTF32: hi*hi + lo*hi + hi*lo, FP32 accumulation.  Bound: tcgen05 issue rate (N <= 64: every MMA sits on the
-// per-instruction floor), which is why two warps issue alternate source rows into alternate TMEM buffers.
+// per-instruction floor), which is why several warps issue alternate source rows into alternate TMEM buffers (each
+// buffer is written by one warp only: the accumulation order is fixed).
 //
 // Roles (448 threads): warps 0-7 stage the activation rows (global -> hi/lo -> shared), warps 8-11 epilogue (thread =
-// output column = TMEM lane), warps 12/13 issue the MMAs of the even / odd source rows.  mbarriers: a_full/a_empty per
+// output column = TMEM lane), warps 12.. issue the MMAs (source row g belongs to issuing warp g % kIssuers).  mbarriers: a_full/a_empty per
 // operand stage, d_full/d_free per TMEM buffer.
 #include "tc_common.cuh"
 
@@ -32,7 +33,11 @@ using tiled::round_up;
 
 constexpr int kTile = 128;
 constexpr int kWorkers = 256;
-constexpr int kThreads = 32 * 14;
+#ifndef TNMF_RC_ISSUERS
+#define TNMF_RC_ISSUERS 4
+#endif
+constexpr int kIssuers = TNMF_RC_ISSUERS;    // MMA-issuing warps: source row g belongs to warp g % kIssuers
+constexpr int kThreads = 32 * (12 + kIssuers);
 constexpr int kMaxStages = 6;
 constexpr int kBufs = 8;            // TMEM buffers of 64 columns
 constexpr int kMaxSmem = 226 * 1024;
@@ -46,6 +51,7 @@ struct Plan {
     int tiles, rblocks, rows_per_block;
     long long units;
     int n_stages, stage_floats, b_floats;   // floats of ONE of the hi / lo halves
+    int n_issuers;                  // issuing warps in use: at most n_stages (see the issuer loop)
     int grid;
     size_t smem;
 };
@@ -76,6 +82,7 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.n_stages = (int)(((size_t)kMaxSmem - fixed) / ((size_t)2 * p.stage_floats * 4));
     if (p.n_stages > kMaxStages) p.n_stages = kMaxStages;
     p.smem = fixed + (size_t)p.n_stages * 2 * p.stage_floats * 4;
+    p.n_issuers = p.n_stages < kIssuers ? p.n_stages : kIssuers;
     const long long cols = (long long)g.N * p.DXP;
     if (cols <= 0 || cols >= (1ll << 31) - kTile) return false;
     p.tiles = (int)((cols + kTile - 1) / kTile);
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(kThreads, 1) recon_tc_kernel(const Geo2 g, con
             if (lane == 0) a.epart[(long long)blockIdx.x * 4 + (warp & 3)] = e_local;
         }
     } else {
-        // ------------------------------------ MMA issuers: warp 12 the even source rows, warp 13 the odd ones ------------------------------------
+        // ------------------------------------ MMA issuers: source row g -> warp 12 + g % kIssuers ------------------------------------
         const int x = warp - 12;
         const unsigned lbo_a = (unsigned)p.RWSp * 16, lbo_b = (unsigned)NP * 16;
         const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
@@ -279,7 +286,9 @@ __global__ void __launch_bounds__(kThreads, 1) recon_tc_kernel(const Geo2 g, con
             const Unit w = make_unit(u, g, p);
             const int ta = max(w.t_lo, 0), tb = min(w.t_hi, g.TY - 1);
             for (int ty = ta; ty <= tb; ++ty, ++g_row) {
-                if ((g_row & 1) != x) continue;
+                // A warp that skips rows only ever tests the parity of a barrier; that is the right phase only while it is
+                // at most one phase away, i.e. while the rows it skips fit into the stage ring: n_issuers <= n_stages.
+                if ((int)(g_row % p.n_issuers) != x) continue;
                 const int st = (int)(g_row % p.n_stages), buf = (int)(g_row % kBufs);
                 if (g_row >= kBufs) mbar_wait(&d_free[buf], (unsigned)(((g_row / kBufs) - 1) & 1));
                 mbar_wait(&a_full[st], (unsigned)((g_row / p.n_stages) & 1));
