@@ -5,6 +5,6 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $CMD > gpurun_out/${T}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_launch.log 2>&1
 $CMD > gpurun_out/${T}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"hupd_tc_kernel|recon_tma_kernel|gradw_tc_kernel" -s 8 -c 4 -o gpurun_out/prof_${T} -f $CMD > gpurun_out/${T}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"hupd_tc_kernel|recon_tc_kernel|gradw_tc_kernel" -s 8 -c 4 -o gpurun_out/prof_${T} -f $CMD > gpurun_out/${T}_ncu_full.log 2>&1
 tail -3 gpurun_out/${T}_ncu_full.log
 ls -la gpurun_out | grep ${T}
