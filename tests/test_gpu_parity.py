@@ -428,7 +428,7 @@ def test_tc_gradient_w_vs_oracle(case, mode):
 @pytest.mark.parametrize('case', range(len(TC_CASES)))
 def test_tc_reconstruct_vs_oracle(case, mode):
     """Tensor-core reconstruction (input-stationary, shifted-operand MMAs, register ring of output rows) and its fused
-    energy against the oracle, plus the strided single-atom view of partial_reconstruct (which the FP32 kernels serve)."""
+    energy against the oracle, plus the strided single-atom view of partial_reconstruct."""
     N, C, M, D, A = TC_CASES[case]
     rng = np.random.default_rng(500 + case)
     V = rng.random((N, C) + D).astype(np.float32)
