@@ -49,7 +49,8 @@ extern "C" {
 #define TNMF_PATH_AUTO    0
 #define TNMF_PATH_GENERIC 1   /* one-thread-per-output kernels, any rank <= 3, float and double */
 #define TNMF_PATH_TILED   2   /* cp.async-staged register-tiled FP32-FMA kernels (rank <= 2, float, all modes) */
-#define TNMF_PATH_TMA     3   /* persistent warp-specialised TMA + mbarrier kernels (rank 2, float, valid/full) */
+#define TNMF_PATH_TMA     3   /* persistent warp-specialised TMA + mbarrier kernels (rank 2, float, valid/full; also
+                               * single-channel rank-1 batches, which run as one 2-D image of signal rows) */
 #define TNMF_PATH_TC      4   /* tcgen05 3xTF32 tensor-core kernels with TMEM accumulators (reconstruction, H gradient /
                                  update, W gradient: rank 2, float, valid/full, atom height <= 15, C * atom width <= 64;
                                  reconstruction: C <= 4, atoms <= 64); operations / shapes without one use the TMA family */

@@ -100,13 +100,29 @@ def test_tiled_path_selection(lib, monkeypatch):
     assert fam(tall_atom, _lib.OP_GRADIENT_H) == _lib.PATHS['tma']               # 'tc' = tensor cores where a kernel exists
     circ = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, 'circular')
     assert [fam(circ, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
+    # single-channel 1-D batches run as one 2-D image of signal rows: TMA wherever the strides are 16-byte multiples
+    # (V and R rows of 1000 floats are; H rows of 1049 floats are not until the backend pads them to 1052)
     one_d = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32)
-    assert [fam(one_d, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
+    assert [fam(one_d, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3          # below 2^20 elements: 1-D kernels
+    big = _lib.make_problem(2048, 1, 64, (4096,), (128,), _lib.TNMF_F32, 'valid', 'auto', 64 * 4224, 4224)   # cfg4
+    assert [fam(big, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
+    monkeypatch.setenv('TNMF_ROWS_VIEW_MIN', '0')
+    assert [fam(one_d, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled'], _lib.PATHS['tma'], _lib.PATHS['tiled']]
+    one_d_padded = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32, 'valid', 'auto', 5 * 1052, 1052)
+    assert [fam(one_d_padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
+    monkeypatch.setenv('TNMF_NO_ROWS_VIEW', '1')
+    assert [fam(one_d_padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
+    monkeypatch.delenv('TNMF_NO_ROWS_VIEW')
+    one_d_2ch = _lib.make_problem(100, 2, 5, (1000,), (50,), _lib.TNMF_F32)
+    assert [fam(one_d_2ch, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
+    one_d_circ = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32, 'circular')
+    assert [fam(one_d_circ, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
     assert fam(f64_2d, _lib.OP_GRADIENT_W) == _lib.PATHS['generic']
     padded.path = _lib.PATHS['tma']
     assert fam(padded, 0) == _lib.PATHS['tma']
     one_d.path = _lib.PATHS['tma']
     assert fam(one_d, 0) == -1
+    monkeypatch.delenv('TNMF_ROWS_VIEW_MIN')
     assert lib.tnmf_workspace_bytes(ctypes.byref(padded)) % 256 == 0
     bad_pitch = _lib.make_problem(2, 1, 2, (16, 16), (3, 3), _lib.TNMF_F32, h_pitch=10)    # narrower than a row
     assert fam(bad_pitch, 0) == -1

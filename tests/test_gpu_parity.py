@@ -284,6 +284,78 @@ def test_tiled_vs_oracle(case, mode):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# single-channel 1-D batches run as ONE 2-D image of signal rows (capi.cu rows_view): the 2-D kernel families against
+# the oracle and against the 1-D kernels (TNMF_NO_ROWS_VIEW=1), whole batches and minibatch slices
+# ---------------------------------------------------------------------------------------------------------
+ROWS_CASES = [
+    # N, M, D, A
+    (5, 7, 300, 128),       # cfg4-like atom
+    (64, 5, 1000, 50),      # cfg1-like, many rows
+    (3, 4, 64, 9),          # short signals
+    (2, 3, 130, 5),         # signal length not a multiple of 4: V/R boxes are not TMA-able
+    (9, 17, 256, 32),       # more than one atom block
+]
+
+
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+@pytest.mark.parametrize('case', range(len(ROWS_CASES)))
+def test_rows_view_1d_vs_oracle(case, mode, monkeypatch):
+    N, M, D, A = ROWS_CASES[case]
+    monkeypatch.setenv('TNMF_ROWS_VIEW_MIN', '0')       # 'auto' takes the view from 2^20 signal elements on
+    rng = np.random.default_rng(700 + case)
+    V = rng.random((N, 1, D)).astype(np.float32)
+    W = rng.random((M, 1, A)).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, (D,), (A,))).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode)
+    assert Hd.stride(1) % 4 == 0 and Hd.stride(0) == M * Hd.stride(1)      # padded rows, [n, m, t] order kept
+    tol = 2e-5
+    for s in (slice(1, N - 1), slice(N - 1, N), slice(None)):
+        Hs64, Vs64 = H64[s], V64[s]
+        if Hs64.shape[0] == 0:
+            continue
+        _close(be.reconstruct(Wd, Hd[s]), orc.reconstruct(W64, Hs64, mode), tol)
+        neg, pos = be.reconstruction_gradient_H(V, Wd, Hd, s)
+        rn, rp = orc.reconstruction_gradient_H(Vs64, W64, Hs64, mode)
+        _close(neg, rn, tol)
+        _close(pos, rp, tol)
+        neg, pos = be.reconstruction_gradient_W(V, Wd, Hd, s)
+        rn, rp = orc.reconstruction_gradient_W(Vs64, W64, Hs64, mode)
+        _close(neg, rn, tol)
+        _close(pos, rp, tol)
+    fam = be.kernel_families()              # of the last problem: the whole batch
+    if case in (1, 4):              # shapes the persistent TMA kernels plan for (case 0: atom too wide for so short a row)
+        assert fam['update_h'] == 'tma', fam
+        if mode == 'valid':
+            assert fam == {'reconstruct': 'tma', 'update_h': 'tma', 'gradient_w': 'tma'}, fam
+    assert np.isclose(be.reconstruction_energy(V, Wd, Hd), orc.reconstruction_energy(V64, W64, H64, mode), rtol=2e-5)
+    # fused updates (all epilogue terms) against the oracle, then against the 1-D kernels on the same inputs
+    nmf = orc.OracleNMF(M, (A,), reconstruction_mode=mode)
+    nmf.V, nmf.W, nmf.H = V64, W64.copy(), H64.copy()
+    # (the rows view serves the update without inhibition terms; with them the dense G arrays keep the 1-D kernels)
+    for s in (slice(0, 1), slice(1, N)):
+        nmf.update_H(s, sparsity=0.1)
+        be.update_H(V, Wd, Hd, s, 0.1)
+    _close(Hd, nmf.H, 5e-5)
+    nmf.update_H(slice(None), sparsity=0.1, inhibition=0.2, cross_inhibition=0.3)
+    be.update_H(V, Wd, Hd, slice(None), 0.1, 0.2, 0.3, nmf.inhibition_kernels)
+    _close(Hd, nmf.H, 1e-4)
+    nmf.update_W()
+    grad = torch.empty((2, *Wd.shape), dtype=Wd.dtype, device=Wd.device)
+    be.apply_W_update(Wd, be.gradient_W(V, Wd, Hd, slice(None), grad))
+    _close(Wd, nmf.W, 5e-5)
+    monkeypatch.setenv('TNMF_NO_ROWS_VIEW', '1')
+    be1, W1, H1 = _backend(V, W, H, mode)
+    for s in (slice(0, 1), slice(1, N)):
+        be1.update_H(V, W1, H1, s, 0.1)
+    be1.update_H(V, W1, H1, slice(None), 0.1, 0.2, 0.3, nmf.inhibition_kernels)
+    assert set(be1.kernel_families().values()) == {'tiled'}
+    be1.apply_W_update(W1, be1.gradient_W(V, W1, H1, slice(None), torch.empty_like(grad)))
+    _close(Hd, H1.cpu().numpy(), 5e-5)
+    _close(Wd, W1.cpu().numpy(), 5e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # persistent TMA kernels against the oracle: 2-D, 'valid' / 'full', sample rows a multiple of 16 bytes
 # ---------------------------------------------------------------------------------------------------------
 TMA_CASES = [

@@ -154,11 +154,13 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         return p, H
 
     def _alloc_H(self, shape, random: bool) -> torch.Tensor:
-        """Activation tensor of the reference's shape [n, M, *T].  For float32 problems with two shift axes the
-        rows are padded to a multiple of 4 elements (16 bytes) - the TMA kernels cut their boxes out of H and need
-        that stride alignment - and the returned tensor is the [..., :T_x] view of the padded buffer."""
+        """Activation tensor of the reference's shape [n, M, *T].  For float32 problems with two shift axes (and
+        single-channel 1-D problems, which the library runs as one 2-D image of signal rows) the rows are padded to a
+        multiple of 4 elements (16 bytes) - the TMA kernels cut their boxes out of H and need that stride alignment -
+        and the returned tensor is the [..., :T_x] view of the padded buffer."""
         pad = (-shape[-1]) % 4
-        if self._dtype != torch.float32 or len(self.atom_shape) != 2 or self._path == 'generic':
+        rows = len(self.atom_shape) == 1 and self.n_channels == 1 and self._reconstruction_mode != 'circular'
+        if self._dtype != torch.float32 or not (len(self.atom_shape) == 2 or rows) or self._path == 'generic':
             pad = 0
         padded = (*shape[:-1], shape[-1] + pad)
         # the storage of the previous fit is reused when the shape repeats (fit_stream, repeated fits): a fresh

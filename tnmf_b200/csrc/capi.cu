@@ -11,7 +11,28 @@ static bool aligned16(const void *p) { return (reinterpret_cast<unsigned long lo
 
 namespace {
 
-int make_geo(const tnmf_problem *p, Geo &g) {
+// A batch of single-channel 1-D signals IS one 2-D image: row n = signal n, atoms one row high (A_y = 1, so rows never
+// mix).  V[n,0,x], R[n,0,x] and W[m,0,a] are already laid out that way; H[n,m,t] becomes the image's activation with
+// the sample stride as its row stride.  The 2-D kernel families (TMA staging, persistent CTAs) then serve the 1-D
+// problems as well - cfg4 (2048 x 4096, 64 atoms x 128): 28.1 -> 23.1 ms per iteration on B200.  Offsets inside one
+// "image" are 32-bit in the tiled kernels, hence the size guard; TNMF_NO_ROWS_VIEW=1 keeps the 1-D kernels,
+// TNMF_ROWS_VIEW_MIN=<elements> moves the batch size from which the view is taken (default 2^20 signal elements).
+void rows_view(const tnmf_problem *p, Geo &g) {
+    if (p->ndim != 1 || g.C != 1 || g.wrap || p->dtype != TNMF_F32 || g.N < 2) return;
+    if ((long long)g.N * g.D[2] >= (1ll << 30) || (long long)g.N * g.T[2] >= (1ll << 30)) return;
+    if (getenv("TNMF_NO_ROWS_VIEW")) return;
+    // small batches do not fill the persistent 2-D kernels (cfg1, 100 x 1000: 0.079 against 0.060 ms per iteration)
+    const char *min_env = getenv("TNMF_ROWS_VIEW_MIN");
+    const long long min_elems = min_env ? atoll(min_env) : (1ll << 20);
+    if ((long long)g.N * g.D[2] < min_elems) return;
+    g.D[1] = g.N; g.T[1] = g.N; g.A[1] = 1; g.off[1] = 0;
+    g.hsy = g.hsn;
+    g.hsn = g.hsn * g.N;
+    g.N = 1;
+    g.ndim = 2;
+}
+
+int make_geo(const tnmf_problem *p, Geo &g, bool allow_rows_view = true) {
     if (!p) return TNMF_EINVAL;
     if (p->ndim < 1 || p->ndim > TNMF_MAX_SHIFT_DIMS) return TNMF_EUNSUPPORTED;
     if (p->dtype != TNMF_F32 && p->dtype != TNMF_F64) return TNMF_EUNSUPPORTED;
@@ -37,6 +58,7 @@ int make_geo(const tnmf_problem *p, Geo &g) {
     const long long tvol = (long long)g.T[0] * g.T[1] * g.hsy;
     g.hsm = p->h_stride_m ? p->h_stride_m : tvol;
     g.hsn = p->h_stride_n ? p->h_stride_n : tvol * g.M;
+    if (allow_rows_view) rows_view(p, g);
     return TNMF_OK;
 }
 
@@ -135,21 +157,26 @@ int tnmf_transform_shape(const tnmf_problem *p, int32_t *t_shape) {
     return TNMF_OK;
 }
 
-size_t tnmf_workspace_bytes(const tnmf_problem *p) {
-    Geo g;
-    if (make_geo(p, g)) return 0;
+static size_t workspace_bytes_of(const Geo &g, int dtype) {
     size_t bytes = energy_partials_bytes(g);
-    if (tiled_supported(g, p->dtype)) {
+    if (tiled_supported(g, dtype)) {
         const size_t t = align256(tiled_workspace_bytes(g));
         if (t > bytes) bytes = t;
     }
-    const size_t t = tma_workspace_bytes(g, p->dtype);
+    const size_t t = tma_workspace_bytes(g, dtype);
     if (t > bytes) bytes = t;
-    if (tc_gradw_supported(g, p->dtype)) {
+    if (tc_gradw_supported(g, dtype)) {
         const size_t w = align256(tc_gradw_workspace_bytes(g));
         if (w > bytes) bytes = w;
     }
     return bytes;
+}
+
+size_t tnmf_workspace_bytes(const tnmf_problem *p) {
+    Geo g, plain;
+    if (make_geo(p, g) || make_geo(p, plain, false)) return 0;
+    const size_t a = workspace_bytes_of(g, p->dtype), b = workspace_bytes_of(plain, p->dtype);
+    return a > b ? a : b;
 }
 
 int tnmf_uses_tiled_path(const tnmf_problem *p) {
@@ -241,7 +268,9 @@ static int gradient_h_dispatch(const tnmf_problem *p, const void *V, const void 
                                void *pos, void *H, double reg, const void *G, double lambda, const void *Gsum,
                                double lambda_cross, void *workspace, size_t workspace_bytes, void *stream) {
     Geo g;
-    int s = make_geo(p, g);
+    // the rows view re-strides H only: dense neg / pos outputs and dense G / Gsum inputs are in the caller's
+    // [n][m][t] order, so the unfused gradient and the inhibition epilogue keep the 1-D geometry
+    int s = make_geo(p, g, !neg && !pos && !G && !Gsum);
     if (s) return s;
     if (!V || !R || !W) return TNMF_EINVAL;
     if (g.N == 0) return TNMF_OK;

@@ -66,8 +66,10 @@ struct Plan {
 
 struct Args {
     const float *V, *R, *H;
-    float *partials;                // [grid][S][2][M*C*AY*AX]
+    float *partials;                // [grid][S][2][M*C*AYW*AX]
     int m0;
+    int ay0, AYW;                   // atom rows [ay0, ay0 + g.AY) of an atom AYW rows high (tall atoms run in row chunks)
+    int accumulate;                 // 1: the slices were zeroed by the host and every drain adds (several launches share them)
 };
 
 bool make_plan(const Geo2 &g, Plan &p) {
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
     __syncthreads();
     tc_fence_after();
 
-    const long long count = (long long)g.M * C * AY * AX;
+    const long long count = (long long)g.M * C * a.AYW * AX;
 
     if (warp < 8) {
         // ------------------------------------ workers ------------------------------------
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
         // ------------------------------------ accumulator drainers ------------------------------------
         // one accumulator set per epoch: lane = operand row k' = (X, c, ax), column = (ay, atom)
         long long rows_done = 0;
-        bool first_drain = true;
+        bool first_drain = !a.accumulate;
         auto drain = [&](long long e) {
             const int set = (int)(e & 1);
             mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100);
@@ -360,8 +362,8 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                 const int ay = AY - 1 - j + sr;                         // stacked row s sees the window one row later
                 if (live && ay >= 0 && ay < AY) {
                     // all 16 running sums are fetched before the first store (stores would otherwise order the loads)
-                    float *dst0 = slice + (((long long)a.m0 * C + c) * AY + ay) * AX + ax;
-                    const long long mstride = (long long)C * AY * AX;
+                    float *dst0 = slice + (((long long)a.m0 * C + c) * a.AYW + a.ay0 + ay) * AX + ax;
+                    const long long mstride = (long long)C * a.AYW * AX;
                     float old[kNB];
 #pragma unroll
                     for (int ml = 0; ml < kNB; ++ml)
@@ -480,26 +482,60 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
 }  // namespace tc
 
 // ---- dispatch ----------------------------------------------------------------------------------------------------------
+// Tall atoms (A_y > 15, 'valid' mode): rows [a0, a0 + h) of the W gradient are the W gradient of an h-row atom against H
+// moved down by A_y - a0 - h rows (H row = d_y + (A_y - 1) - a_y = d_y + (h - 1 - a') + (A_y - a0 - h)), so the atom is cut
+// into row chunks that the kernel above serves one after the other.  All chunks add into the same zeroed per-CTA slices
+// (disjoint entries), and one fixed-order finish sums them: still deterministic, no atomics.
+namespace tc {
+namespace gw {
+static Geo2 chunk_geo(const Geo2 &q, int h) {
+    Geo2 s = q;
+    s.AY = h; s.TY = q.DY + h - 1; s.offy = h - 1;
+    return s;
+}
+static bool plan_tall(const Geo2 &q, int &h, int &n) {
+    if (q.AY <= 15 || q.wrap || q.offy != q.AY - 1 || q.TY != q.DY + q.AY - 1) return false;
+    Plan p;
+    for (h = 15; h >= 2; --h)
+        if (make_plan(chunk_geo(q, h), p)) break;
+    if (h < 2) return false;
+    n = ceil_div(q.AY, h);
+    h = ceil_div(q.AY, n);                                      // balanced chunks; the last one may be shorter
+    for (int a0 = 0; a0 < q.AY; a0 += h)
+        if (!make_plan(chunk_geo(q, q.AY - a0 < h ? q.AY - a0 : h), p)) return false;
+    return true;
+}
+}  // namespace gw
+}  // namespace tc
+
 bool tc_gradw_supported(const Geo &g, int dtype) {
     if (dtype != TNMF_F32 || g.wrap) return false;
     if (g.D[0] != 1 || g.A[0] != 1 || g.T[0] != 1) return false;      // rank <= 2
     if (g.D[1] == 1 && g.A[1] == 1) return false;                     // rank 1: the FP32 kernels serve it
     if (g.N < 1) return false;
     tc::gw::Plan p;
-    return tc::gw::make_plan(tiled::make_geo2(g), p);
+    const tiled::Geo2 q = tiled::make_geo2(g);
+    int h, n;
+    return tc::gw::make_plan(q, p) || tc::gw::plan_tall(q, h, n);
 }
 
 size_t tc_gradw_workspace_bytes(const Geo &g) {
     tc::gw::Plan p;
-    if (!tc::gw::make_plan(tiled::make_geo2(g), p)) return 0;
-    return (size_t)p.grid * p.S * 2 * (size_t)g.M * g.C * g.A[1] * g.A[2] * sizeof(float);
+    const tiled::Geo2 q = tiled::make_geo2(g);
+    const size_t slice = 2 * (size_t)g.M * g.C * g.A[1] * g.A[2] * sizeof(float);
+    if (tc::gw::make_plan(q, p)) return (size_t)p.grid * p.S * slice;
+    int h, n;
+    if (tc::gw::plan_tall(q, h, n)) return (size_t)tma::sm_count() * 2 * slice;     // any grid, any stacking
+    return 0;
 }
 
 int tc_gradient_w(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
                   size_t workspace_bytes, cudaStream_t st) {
     const tiled::Geo2 q = tiled::make_geo2(g);
     tc::gw::Plan p;
-    if (!tc::gw::make_plan(q, p)) return TNMF_EUNSUPPORTED;
+    int h = 0, n = 0;
+    const bool whole = tc::gw::make_plan(q, p);
+    if (!whole && !tc::gw::plan_tall(q, h, n)) return TNMF_EUNSUPPORTED;
     const long long count = (long long)g.M * g.C * g.A[1] * g.A[2];
     if (!workspace || workspace_bytes < tc_gradw_workspace_bytes(g)) return TNMF_EWORKSPACE;
     cudaError_t e = cudaFuncSetAttribute(tc::gw::gradw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -507,14 +543,40 @@ int tc_gradient_w(const Geo &g, const float *V, const float *R, const float *H, 
     if (e != cudaSuccess) return status_from_cuda(e);
     tc::gw::Args a;
     a.V = V; a.R = R; a.H = H; a.partials = (float *)workspace;
-    for (int m0 = 0; m0 < g.M; m0 += tc::gw::kNB) {
-        a.m0 = m0;
-        tc::gw::gradw_tc_kernel<<<(unsigned)p.grid, tc::gw::kThreads, p.smem, st>>>(q, p, a);
-        TNMF_CHECK_LAUNCH();
+    a.ay0 = 0; a.AYW = q.AY; a.accumulate = 0;
+    if (whole) {
+        for (int m0 = 0; m0 < g.M; m0 += tc::gw::kNB) {
+            a.m0 = m0;
+            tc::gw::gradw_tc_kernel<<<(unsigned)p.grid, tc::gw::kThreads, p.smem, st>>>(q, p, a);
+            TNMF_CHECK_LAUNCH();
+        }
+        return finish_gradient_w<float>((const float *)workspace, p.grid * p.S, count, neg, pos, st);
     }
-    return finish_gradient_w<float>((const float *)workspace, p.grid * p.S, count, neg, pos, st);
+    const int slices = tma::sm_count() * 2;
+    e = cudaMemsetAsync(workspace, 0, (size_t)slices * 2 * count * sizeof(float), st);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    a.accumulate = 1;
+    for (int a0 = 0; a0 < q.AY; a0 += h) {
+        const int hc = q.AY - a0 < h ? q.AY - a0 : h;
+        const tiled::Geo2 sub = tc::gw::chunk_geo(q, hc);
+        if (!tc::gw::make_plan(sub, p)) return TNMF_EUNSUPPORTED;
+        a.ay0 = a0;
+        a.H = H + (long long)(q.AY - a0 - hc) * q.hsy;
+        for (int m0 = 0; m0 < g.M; m0 += tc::gw::kNB) {
+            a.m0 = m0;
+            tc::gw::gradw_tc_kernel<<<(unsigned)p.grid, tc::gw::kThreads, p.smem, st>>>(sub, p, a);
+            TNMF_CHECK_LAUNCH();
+        }
+    }
+    return finish_gradient_w<float>((const float *)workspace, slices, count, neg, pos, st);
 }
 
-int tc_gradw_launches(const Geo &g) { return tiled::ceil_div(g.M, tc::gw::kNB) + 1; }
+int tc_gradw_launches(const Geo &g) {
+    const tiled::Geo2 q = tiled::make_geo2(g);
+    tc::gw::Plan p;
+    int h = 0, n = 1;
+    if (!tc::gw::make_plan(q, p)) tc::gw::plan_tall(q, h, n);
+    return n * tiled::ceil_div(g.M, tc::gw::kNB) + 1;
+}
 
 }  // namespace tnmf
