@@ -496,6 +496,48 @@ def test_tc_gradient_w_vs_oracle(case, mode):
     _close(Wd, nmf.W, 5e-5)
 
 
+TALL_CASES = [
+    # N, C, M, D, A  - atoms higher than the 15 rows one launch takes: the W gradient runs in atom-row chunks ('valid')
+    (2, 1, 8, (40, 72), (20, 30)),      # two balanced chunks of 10 rows
+    (1, 2, 5, (50, 64), (33, 16)),      # three chunks, two channels, partial atom block
+    (3, 1, 4, (30, 40), (16, 5)),       # one row more than a launch takes; narrow atom (two stacked source rows)
+    (1, 1, 8, (96, 128), (64, 64)),     # cfg5's atoms: all 128 MMA lanes carry taps
+    (2, 1, 20, (40, 70), (31, 12)),     # two atom blocks x three chunks, last chunk shorter
+]
+
+
+@pytest.mark.parametrize('case', range(len(TALL_CASES)))
+def test_tc_gradient_w_tall_atoms_vs_oracle(case):
+    N, C, M, D, A = TALL_CASES[case]
+    mode = 'valid'
+    rng = np.random.default_rng(450 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    be.reconstruct(Wd, Hd)
+    assert be.kernel_families()['gradient_w'] == 'tc'
+    rn, rp = orc.reconstruction_gradient_W(V64, W64, H64, mode)
+    for _ in range(2):                  # twice: the second call finds the workspace dirty
+        neg, pos = be.reconstruction_gradient_W(V, Wd, Hd)
+        _close(neg, rn, 2e-5)
+        _close(pos, rp, 2e-5)
+    if N > 2:
+        neg, pos = be.reconstruction_gradient_W(V, Wd, Hd, slice(1, N - 1))
+        rn, rp = orc.reconstruction_gradient_W(V64[1:N - 1], W64, H64[1:N - 1], mode)
+        _close(neg, rn, 2e-5)
+        _close(pos, rp, 2e-5)
+    # bitwise run-to-run determinism (fixed-order finish over zero-initialised per-CTA slices)
+    a = torch.stack(be.reconstruction_gradient_W(V, Wd, Hd))
+    b = torch.stack(be.reconstruction_gradient_W(V, Wd, Hd))
+    assert torch.equal(a, b)
+    # 'full' mode has no chunked form: the FP32 kernels keep serving it
+    be2, W2, H2 = _backend(V, W, rng.random((N, M) + orc.transform_shape('full', D, A)).astype(np.float32), 'full', 'tc')
+    be2.reconstruct(W2, H2)
+    assert be2.kernel_families()['gradient_w'] != 'tc'
+
+
 @pytest.mark.parametrize('mode', ('valid', 'full'))
 @pytest.mark.parametrize('case', range(len(TC_CASES)))
 def test_tc_reconstruct_vs_oracle(case, mode):

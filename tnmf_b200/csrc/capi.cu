@@ -87,8 +87,10 @@ bool tc_gradw_worthwhile(const Geo &g) {
     if (getenv("TNMF_NO_TC") || getenv("TNMF_NO_TC_GRADW")) return false;
     const int kp = (g.C * g.A[2] + 7) / 8 * 8, mp = (g.M + 15) / 16 * 16;
     const int stack = (4 * kp <= 128 && 16 * (g.A[1] + 1) <= 256) ? 2 : 1;
+    // atoms higher than 15 rows run in row chunks that expand V and R once per chunk: measured no faster than the FP32
+    // kernel (cfg5: 11.2 against 11.0 ms), so 'auto' leaves them there; kernel_path='tc' still takes the chunked form
     return 2 * stack * kp >= 64 && g.C * g.A[2] * 2 >= kp && (double)g.M / mp >= 0.5 && (long long)g.N * g.T[2] >= 64 &&
-           g.A[1] >= 3;
+           g.A[1] >= 3 && g.A[1] <= 15;
 }
 
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;
