@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TNMF_ABI_VERSION 2
+#define TNMF_ABI_VERSION 3
 #define TNMF_MAX_SHIFT_DIMS 3
 
 /* element types */
@@ -101,6 +101,10 @@ int tnmf_uses_tiled_path(const tnmf_problem *p);
 /* The TNMF_PATH_* family that serves operation `op` (TNMF_OP_*) of this problem, or -1 if the problem is malformed /
  * the forced `path` cannot serve it. */
 int tnmf_kernel_family(const tnmf_problem *p, int op);
+
+/* How many kernels one call of operation `op` launches for this problem (the fused / unfused H operations alike), or -1
+ * like tnmf_kernel_family.  Bookkeeping for callers that report launch counts (bench.py's "gpu_launches"). */
+int tnmf_launch_count(const tnmf_problem *p, int op);
 
 /* R[n,c,d] = sum_m sum_a W[m,c,a] * Hpad[n,m,d+p-a].
  * Replaces Backend.reconstruct, tnmf/backends/_Backend.py:120-122 (NumPy.py:122-132, PyTorch.py:26-43). */

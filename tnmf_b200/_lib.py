@@ -29,7 +29,7 @@ MODES = {'valid': 0, 'full': 1, 'circular': 2}
 PATHS = {'auto': 0, 'generic': 1, 'tiled': 2, 'tma': 3, 'tc': 4}
 OP_RECONSTRUCT, OP_GRADIENT_H, OP_GRADIENT_W = 0, 1, 2
 TNMF_OK, TNMF_EINVAL, TNMF_EUNSUPPORTED, TNMF_EWORKSPACE, TNMF_ECUDA = 0, 1, 2, 3, 1000
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class Problem(ctypes.Structure):
@@ -54,6 +54,7 @@ SIGNATURES = {
     'tnmf_workspace_bytes': (_sz, [_P]),
     'tnmf_uses_tiled_path': (ctypes.c_int, [_P]),
     'tnmf_kernel_family': (ctypes.c_int, [_P, ctypes.c_int]),
+    'tnmf_launch_count': (ctypes.c_int, [_P, ctypes.c_int]),
     'tnmf_reconstruct': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _sz, _vp]),
     'tnmf_reconstruct_energy': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'tnmf_gradient_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -337,14 +337,9 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         return R
 
     def _n_launches(self, p: _lib.Problem, op: int) -> int:
-        """Kernels one call of operation `op` launches (the TMA family pre-arranges the atoms in a tiny extra
-        kernel; the W gradient always has its finishing reduction)."""
-        fam = int(self._lib.tnmf_kernel_family(ctypes.byref(p), op))
-        if op == _lib.OP_GRADIENT_W:
-            return (p.n_atoms + 15) // 16 + 1 if fam == _lib.PATHS['tc'] else 2
-        if fam == _lib.PATHS['tc']:
-            return 1 if op == _lib.OP_RECONSTRUCT else (p.n_atoms + 15) // 16    # H update: one launch per 16 atoms
-        return 2 if fam == _lib.PATHS['tma'] else 1
+        """Kernels one call of operation `op` launches (the TMA family pre-arranges the atoms in a tiny extra kernel, the
+        tensor-core kernels take 16 atoms per launch, the W gradient always has its finishing reduction)."""
+        return max(int(self._lib.tnmf_launch_count(ctypes.byref(p), op)), 0)
 
     def reconstruction_gradient_H(self, V, W, H, s: slice = sliceNone):
         """(neg, pos) with the shape of H[s]   (tnmf/backends/_Backend.py:110-118)."""

@@ -197,6 +197,18 @@ int tnmf_kernel_family(const tnmf_problem *p, int op) {
     return choose_family(p, g, op, &err);
 }
 
+int tnmf_launch_count(const tnmf_problem *p, int op) {
+    Geo g;
+    if (make_geo(p, g)) return -1;
+    if (op < TNMF_OP_RECONSTRUCT || op > TNMF_OP_GRADIENT_W) return -1;
+    int err;
+    const int f = choose_family(p, g, op, &err);
+    if (f < 0) return -1;
+    if (op == TNMF_OP_GRADIENT_W) return f == TNMF_PATH_TC ? tc_gradw_launches(g) : 2;      // + the finishing reduction
+    if (f == TNMF_PATH_TC) return op == TNMF_OP_RECONSTRUCT ? 1 : tc_hupd_launches(g);
+    return f == TNMF_PATH_TMA ? 2 : 1;                                                      // + the atom pre-arrangement
+}
+
 int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *R, void *workspace,
                      size_t workspace_bytes, void *stream) {
     Geo g;
