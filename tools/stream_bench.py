@@ -6,6 +6,9 @@ to subsample.  Prints one JSON line; the timed region contains every host-to-dev
 
     python tools/stream_bench.py [--signals 16384] [--length 4096] [--atoms 64] [--width 128]
                                  [--subsample 4096] [--batch 1024] [--epochs 3]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/stream_bench.py ...
+        one process per GPU: every rank streams its own `--signals` signals, the W gradient is all-reduced once per
+        epoch, the rate is the job's (all ranks' signals over the slowest rank's time)
 
 `--signals` defaults to 16384 (268 MB of pinned host memory), not BASELINE's 1 M (16 GB): the rate is per signal and
 the stream is consumed subsample by subsample, so the total length only changes the run time.
@@ -36,14 +39,20 @@ def main():
                     help="'numpy' = the reference's float64 host draw of H per subsample (8.8 GB and ~9 s per 4096 signals)")
     a = ap.parse_args()
 
-    g = torch.Generator().manual_seed(0)
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    if world > 1:           # torchrun: one process per GPU, every rank streams its own `--signals` signals
+        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+        torch.distributed.init_process_group('nccl')
+    g = torch.Generator().manual_seed(rank)
     V = torch.rand((a.signals, 1, a.length), generator=g, dtype=torch.float32).pin_memory()
     kw = dict(algorithm=MiniBatchAlgorithm.Cyclic_MU, subsample_size=a.subsample, batch_size=a.batch,
               n_epochs=a.epochs, progress_callback=lambda *_: True)
 
     def run(source):
         np.random.seed(0)
-        nmf = TransformInvariantNMF(n_atoms=a.atoms, atom_shape=(a.width,), backend='b200', init=a.init)
+        nmf = TransformInvariantNMF(n_atoms=a.atoms, atom_shape=(a.width,), backend='b200', init=a.init,
+                                    input_is_local_shard=world > 1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         nmf.fit(source, **kw)
@@ -53,18 +62,28 @@ def main():
 
     run(V[:2 * a.subsample])                      # warm-up: module load, pinned staging, allocator
     dt, w, nmf = run(V)
+    if world > 1:           # the job is as slow as its slowest rank
+        t = torch.tensor([dt], dtype=torch.float64, device='cuda')
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dt = float(t.item())
+        w0 = torch.from_numpy(w).cuda()
+        torch.distributed.broadcast(w0, 0)
+        assert torch.equal(w0.cpu(), torch.from_numpy(w)), 'the dictionary differs between ranks'
     n_sub = -(-a.signals // a.subsample)
-    sample_iters = a.signals * a.epochs
+    sample_iters = a.signals * a.epochs * world
     line = {
         'metric': 'sample-iterations/sec, streamed Cyclic-MU fit from pinned host memory (cfg4 shape)',
-        'value': sample_iters / dt, 'unit': 'sample-iterations/s', 'n_gpus': 1, 'seconds': dt,
-        'config': {'signals': a.signals, 'length': a.length, 'atoms': a.atoms, 'atom_width': a.width,
+        'value': sample_iters / dt, 'unit': 'sample-iterations/s', 'n_gpus': world, 'seconds': dt,
+        'config': {'signals_per_gpu': a.signals, 'length': a.length, 'atoms': a.atoms, 'atom_width': a.width,
                    'subsample_size': a.subsample, 'batch_size': a.batch, 'n_epochs': a.epochs, 'subsamples': n_sub, 'init': a.init},
-        'h2d_bytes': int(V.numel() * 4), 'h2d_gbs_needed': V.numel() * 4 / dt / 1e9,
+        'h2d_bytes_per_gpu': int(V.numel() * 4), 'h2d_gbs_per_gpu': V.numel() * 4 / dt / 1e9,
         'kernel_path': nmf._backend.kernel_families(),
         'W_finite': bool(np.isfinite(w).all()), 'W_rows_sum_to_one': bool(np.allclose(w.sum(axis=-1), 1, atol=1e-4)),
     }
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':
