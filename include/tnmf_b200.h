@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TNMF_ABI_VERSION 3
+#define TNMF_ABI_VERSION 4
 #define TNMF_MAX_SHIFT_DIMS 3
 
 /* element types */
@@ -54,6 +54,17 @@ extern "C" {
 #define TNMF_PATH_TC      4   /* tcgen05 3xTF32 tensor-core kernels with TMEM accumulators (reconstruction, H gradient /
                                  update, W gradient: rank 2, float, valid/full, atom height <= 15, C * atom width <= 64;
                                  reconstruction: C <= 4, atoms <= 64); operations / shapes without one use the TMA family */
+
+/* tnmf_problem.flags: switches of the 'auto' family choice (diagnostics / tests; 0 = the library's defaults).  They are part
+ * of the problem description so that every behaviour of the library is reproducible through this interface alone. */
+#define TNMF_FLAG_NO_ROWS_VIEW     1   /* single-channel rank-1 batches keep the rank-1 kernels */
+#define TNMF_FLAG_ROWS_VIEW_ALWAYS 2   /* ... or run as one 2-D image of signal rows whatever the batch size (default: from
+                                        * 2^20 signal elements on) */
+#define TNMF_FLAG_NO_TC_HUPD       4   /* 'auto' keeps the H gradient / update off the tensor-core kernels */
+#define TNMF_FLAG_NO_TC_RECON      8   /* ... the reconstruction */
+#define TNMF_FLAG_NO_TC_GRADW     16   /* ... the W gradient */
+#define TNMF_FLAG_NO_TC           28   /* all three */
+#define TNMF_FLAG_NO_TMA          32   /* 'auto' skips the TMA family (cp.async tiled kernels instead) */
 
 /* operations, for tnmf_kernel_family() */
 #define TNMF_OP_RECONSTRUCT 0
@@ -82,6 +93,8 @@ typedef struct tnmf_problem {
     int32_t atom_shape[TNMF_MAX_SHIFT_DIMS];    /* A                                                 */
     int64_t h_stride_n;                         /* element strides of H's axes 0 and 1; 0 = contiguous */
     int64_t h_stride_m;
+    int32_t flags;                              /* TNMF_FLAG_* (0 = defaults)                        */
+    int32_t reserved;                           /* must be 0                                         */
 } tnmf_problem;
 
 int         tnmf_abi_version(void);

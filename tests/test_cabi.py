@@ -29,9 +29,9 @@ def test_header_and_binding_agree(lib):
 
 
 def test_struct_layout_matches_header():
-    # 8 int32 + 2*3 int32 + 2 int64 = 72 bytes, no padding surprises
-    assert ctypes.sizeof(_lib.Problem) == 8 * 4 + 6 * 4 + 2 * 8
-    assert _lib.Problem.h_stride_n.offset == 56
+    # 8 int32 + 2*3 int32 + 2 int64 + 2 int32 = 80 bytes, no padding surprises
+    assert ctypes.sizeof(_lib.Problem) == 8 * 4 + 6 * 4 + 2 * 8 + 2 * 4
+    assert _lib.Problem.h_stride_n.offset == 56 and _lib.Problem.flags.offset == 72
 
 
 @pytest.mark.parametrize('mode,expected', [('valid', (24, 18)), ('full', (16, 16)), ('circular', (20, 17))])
@@ -68,7 +68,7 @@ def test_status_translation(lib):
     _lib.check(0)
 
 
-def test_tiled_path_selection(lib, monkeypatch):
+def test_tiled_path_selection(lib):
     f32_2d = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32)
     f64_2d = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F64)
     f32_3d = _lib.make_problem(2, 1, 2, (8, 8, 8), (3, 3, 3), _lib.TNMF_F32)
@@ -80,18 +80,25 @@ def test_tiled_path_selection(lib, monkeypatch):
     fam = lambda p, op: lib.tnmf_kernel_family(ctypes.byref(p), op)
     assert fam(f32_2d, _lib.OP_GRADIENT_H) == _lib.PATHS['tc']
     assert fam(f32_2d, _lib.OP_RECONSTRUCT) == _lib.PATHS['tc']
-    monkeypatch.setenv('TNMF_NO_TC_RECON', '1')
+    # the switches of the family choice travel in tnmf_problem.flags (nothing is read from the environment)
+    f32_2d.flags = _lib.FLAG_NO_TC_RECON
     assert fam(f32_2d, _lib.OP_RECONSTRUCT) == _lib.PATHS['tiled']
+    f32_2d.flags = 0
     padded = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, h_pitch=268)
+    padded.flags = _lib.FLAG_NO_TC_RECON
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma'], _lib.PATHS['tc'], _lib.PATHS['tc']]
-    monkeypatch.delenv('TNMF_NO_TC_RECON')
+    padded.flags = 0
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tc']] * 3
-    monkeypatch.setenv('TNMF_NO_TC_GRADW', '1')
+    padded.flags = _lib.FLAG_NO_TC_GRADW
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tc'], _lib.PATHS['tc'], _lib.PATHS['tma']]
-    monkeypatch.delenv('TNMF_NO_TC_GRADW')
-    monkeypatch.setenv('TNMF_NO_TC', '1')
+    padded.flags = _lib.FLAG_NO_TC
     assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
-    monkeypatch.delenv('TNMF_NO_TC')
+    padded.flags = _lib.FLAG_NO_TC | _lib.FLAG_NO_TMA
+    assert [fam(padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
+    padded.flags = 0
+    padded.reserved = 1
+    assert fam(padded, 0) == -1
+    padded.reserved = 0
     few_atoms = _lib.make_problem(8, 1, 3, (64, 64), (5, 5), _lib.TNMF_F32)       # 3 of 16 atoms, K 5 of 8: FP32 kernels
     assert fam(few_atoms, _lib.OP_GRADIENT_H) == _lib.PATHS['tma']
     tall_atom = _lib.make_problem(8, 2, 16, (64, 64), (16, 7), _lib.TNMF_F32)    # 16 atom rows do not fit the TMEM ring
@@ -106,13 +113,13 @@ def test_tiled_path_selection(lib, monkeypatch):
     assert [fam(one_d, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3          # below 2^20 elements: 1-D kernels
     big = _lib.make_problem(2048, 1, 64, (4096,), (128,), _lib.TNMF_F32, 'valid', 'auto', 64 * 4224, 4224)   # cfg4
     assert [fam(big, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
-    monkeypatch.setenv('TNMF_ROWS_VIEW_MIN', '0')
+    one_d.flags = _lib.FLAG_ROWS_VIEW_ALWAYS
     assert [fam(one_d, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled'], _lib.PATHS['tma'], _lib.PATHS['tiled']]
-    one_d_padded = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32, 'valid', 'auto', 5 * 1052, 1052)
+    one_d_padded = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32, 'valid', 'auto', 5 * 1052, 1052,
+                                     flags=_lib.FLAG_ROWS_VIEW_ALWAYS)
     assert [fam(one_d_padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tma']] * 3
-    monkeypatch.setenv('TNMF_NO_ROWS_VIEW', '1')
+    one_d_padded.flags = _lib.FLAG_NO_ROWS_VIEW
     assert [fam(one_d_padded, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
-    monkeypatch.delenv('TNMF_NO_ROWS_VIEW')
     one_d_2ch = _lib.make_problem(100, 2, 5, (1000,), (50,), _lib.TNMF_F32)
     assert [fam(one_d_2ch, op) for op in (0, 1, 2)] == [_lib.PATHS['tiled']] * 3
     one_d_circ = _lib.make_problem(100, 1, 5, (1000,), (50,), _lib.TNMF_F32, 'circular')
@@ -122,7 +129,6 @@ def test_tiled_path_selection(lib, monkeypatch):
     assert fam(padded, 0) == _lib.PATHS['tma']
     one_d.path = _lib.PATHS['tma']
     assert fam(one_d, 0) == -1
-    monkeypatch.delenv('TNMF_ROWS_VIEW_MIN')
     assert lib.tnmf_workspace_bytes(ctypes.byref(padded)) % 256 == 0
     bad_pitch = _lib.make_problem(2, 1, 2, (16, 16), (3, 3), _lib.TNMF_F32, h_pitch=10)    # narrower than a row
     assert fam(bad_pitch, 0) == -1

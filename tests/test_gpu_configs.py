@@ -1,0 +1,164 @@
+"""
+GPU parity at the geometries bench.py times (run on the B200 box with `-m gpu`).
+
+north_star (BASELINE.json): "from identical seeded initialisation against the reference numpy backend on the same
+inputs: energy trajectory within 1e-4 relative and W/H within 1e-3 max-relative after 100 iterations, with the
+tolerance stated per config".  Every BASELINE configuration is run here at its full per-sample geometry (sample shape,
+channels, atoms, atom shape) with the number of samples reduced so that the float64 CPU oracle finishes in seconds,
+on `kernel_path='auto'` - and the test asserts that 'auto' picks, for the reduced batch, the SAME kernel family per
+operation as for the batch bench.py times, so the kernels compared with the oracle are the benchmarked ones.
+
+Per-config tolerances:
+    energy trajectory   max_i |E_i - Eref_i| / Eref_i          <= 1e-4     (all configs)
+    dictionary          max|W - Wref| / max|Wref|              <= 1e-3
+    activations         max|H - Href| / max|Href|              <= 1e-3
+(max-relative = relative to the largest reference entry: the multiplicative update drives many activations towards
+1e-30, where an elementwise relative error is meaningless - two float32 runs of the REFERENCE differ by 1.4e-3 there,
+SURVEY 7.)  The oracle runs in float64 (OracleNMF_FFT, the Fourier-domain restatement pinned to the reference's
+numpy_fft backend by tests/test_oracle.py); the GPU runs in float32 with 3xTF32 tensor-core products.
+
+Second part: the multi-rank path with the REAL kernels - two ranks (gloo, both on cuda:0) run the sharded
+`TransformInvariantNMF` and must reproduce the single-GPU fit and the oracle.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tnmf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+# name: (samples here, iterations, backend kwargs)   - geometry and the benched sample count come from bench.WORKLOADS
+CONFIGS = {
+    'cfg1': (100, 100, {}),
+    'cfg2': (2, 100, {}),
+    'cfg3': (4, 100, {}),
+    'cfg4': (8, 100, dict(rows_view=True)),    # bench: 2048 signals >= 2^20 elements take the rows view by themselves
+    'cfg5': (1, 20, {}),                       # 512 x 512, atoms 64 x 64: 20 iterations keep the oracle at seconds
+}
+TOL_E, TOL_W, TOL_H = 1e-4, 1e-3, 1e-3
+
+
+@pytest.mark.parametrize('name', list(CONFIGS))
+def test_config_parity_against_oracle(name):
+    import bench
+    from tnmf_b200 import TransformInvariantNMF
+    w = bench.WORKLOADS[name]
+    n, iters, kw = CONFIGS[name]
+    rng = np.random.default_rng(11)
+    V = rng.random((n, w['C'], *w['D']), dtype=np.float32)
+
+    np.random.seed(17)
+    ref = orc.OracleNMF_FFT(n_atoms=w['M'], atom_shape=w['A'])
+    e_ref = []
+    ref.fit_batch(V.astype(np.float64), n_iterations=iters,
+                  progress_callback=lambda m, i: e_ref.append(float(m.energy())) or True)
+
+    np.random.seed(17)
+    nmf = TransformInvariantNMF(n_atoms=w['M'], atom_shape=w['A'], backend='b200', init='numpy', kernel_path='auto', **kw)
+    e_gpu = []
+    nmf.fit(V, n_iterations=iters, progress_callback=lambda m, i: e_gpu.append(m._energy_function()) or True)
+    be = nmf._backend
+    fam_here = be.kernel_families()
+    fam_bench = be.kernel_families(w['N'])
+    print(f'{name}: kernel families {fam_here}; bench batch ({w["N"]} samples): {fam_bench}')
+    assert fam_here == fam_bench, 'the reduced batch must run the kernel families bench.py times'
+
+    e_ref, e_gpu = np.asarray(e_ref), np.asarray(e_gpu)
+    e_err = float(np.max(np.abs(e_gpu - e_ref) / e_ref))
+    w_err = float(np.abs(nmf.W - ref.W).max() / np.abs(ref.W).max())
+    h_err = float(np.abs(nmf.H - ref.H).max() / np.abs(ref.H).max())
+    print(f'{name}: {iters} iterations, energy {e_gpu[-1]:.6g} (oracle {e_ref[-1]:.6g})  trajectory err {e_err:.2e}  '
+          f'W err {w_err:.2e}  H err {h_err:.2e}')
+    assert e_err <= TOL_E and w_err <= TOL_W and h_err <= TOL_H
+
+
+# ---------------------------------------------------------------------------------------------------------
+# two ranks, real kernels
+# ---------------------------------------------------------------------------------------------------------
+def _free_port():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        return s.getsockname()[1]
+
+
+def _rank_main(rank, world, port, V, seeds, kw_fit, local, out):
+    import torch.distributed as dist
+    from tnmf_b200 import TransformInvariantNMF
+    from tnmf_b200.distributed import shard_bounds
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(0)                    # both ranks share the one GPU of the box; gloo carries CUDA tensors
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        np.random.seed(seeds[rank])
+        nmf = TransformInvariantNMF(n_atoms=6, atom_shape=(5, 4), backend='b200', init='numpy', distributed=True,
+                                    input_is_local_shard=local)
+        lo, hi = shard_bounds(V.shape[0], world, rank)
+        energies = []
+        nmf.fit(V[lo:hi] if local else V, progress_callback=lambda m, i: energies.append(m._energy_function()) or True,
+                **kw_fit)
+        assert nmf._sharding.is_sharded and nmf.H.shape[0] == hi - lo
+        # the dictionary must be bit-identical on all ranks
+        w0 = nmf.W_device.clone()
+        dist.broadcast(w0, 0)
+        assert torch.equal(w0, nmf.W_device)
+        out[rank] = (nmf.W, nmf.H, energies)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_two_ranks_equal_single_gpu_and_oracle(dtype):
+    """Global V on every rank (the default sharded mode), identically seeded ranks: shards + all-reduce == one GPU ==
+    oracle.  float64 differs by summation order only; float32 within the north_star tolerances."""
+    import torch.multiprocessing as mp
+    from tnmf_b200 import TransformInvariantNMF
+    rng = np.random.default_rng(3)
+    V = rng.random((5, 2, 24, 20)).astype(dtype)        # odd N: shards of 3 and 2 samples
+    kw_fit = dict(n_iterations=12, sparsity_H=0.05)
+
+    np.random.seed(21)
+    ref = orc.OracleNMF(n_atoms=6, atom_shape=(5, 4))
+    e_ref = []
+    ref.fit_batch(V.astype(np.float64), progress_callback=lambda m, i: e_ref.append(float(m.energy())) or True, **kw_fit)
+    np.random.seed(21)
+    one = TransformInvariantNMF(n_atoms=6, atom_shape=(5, 4), backend='b200', init='numpy', distributed=False)
+    one.fit(V, **kw_fit)
+
+    world = 2
+    ctx = mp.get_context('spawn')
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_rank_main, args=(world, _free_port(), V, (21, 21), kw_fit, False, out), nprocs=world, join=True)
+        results = [out[r] for r in range(world)]
+    rtol = 1e-9 if dtype == np.float64 else 1e-4
+    wtol = 1e-9 if dtype == np.float64 else 1e-3
+    from tnmf_b200.distributed import shard_bounds
+    for rank, (W, H, energies) in enumerate(results):
+        lo, hi = shard_bounds(V.shape[0], world, rank)
+        assert np.allclose(energies, e_ref, rtol=rtol)
+        for got, single, want in ((W, one.W, ref.W), (H, one.H[lo:hi], ref.H[lo:hi])):
+            assert np.abs(got - want).max() <= wtol * np.abs(want).max()
+            assert np.abs(got - single).max() <= wtol * np.abs(single).max()
+
+
+def test_two_ranks_unseeded_start_from_one_dictionary():
+    """ranks whose numpy generators differ must still start from rank 0's dictionary.  Every rank
+    passes its own samples; W stays bit-identical across ranks (asserted inside the ranks) and the fit descends."""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(4)
+    V = rng.random((6, 2, 24, 20)).astype(np.float32)
+    world = 2
+    ctx = mp.get_context('spawn')
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_rank_main, args=(world, _free_port(), V, (100, 200), dict(n_iterations=8), True, out), nprocs=world,
+                 join=True)
+        results = [out[r] for r in range(world)]
+    assert np.array_equal(results[0][0], results[1][0])
+    e = results[0][2]
+    assert np.allclose(e, results[1][2], rtol=1e-12) and all(b <= a * (1 + 1e-6) for a, b in zip(e, e[1:]))

@@ -22,9 +22,9 @@ MODES = ('valid', 'full', 'circular')
 REFERENCE_TEST_1D_ENERGIES = {'valid': 2.34946, 'full': 1.87180, 'circular': 3.13228}   # tnmf/tests/test_1d.py:17-22
 
 
-def _backend(V, W, H, mode='valid', path='auto'):
+def _backend(V, W, H, mode='valid', path='auto', **kw):
     from tnmf_b200 import B200_Backend
-    be = B200_Backend(reconstruction_mode=mode, kernel_path=path)
+    be = B200_Backend(reconstruction_mode=mode, kernel_path=path, **kw)
     state = np.random.get_state()
     Wd, Hd = be.initialize(V, W.shape[2:], W.shape[0], None, tuple(range(-(W.ndim - 2), 0)))
     np.random.set_state(state)
@@ -285,7 +285,7 @@ def test_tiled_vs_oracle(case, mode):
 
 # ---------------------------------------------------------------------------------------------------------
 # single-channel 1-D batches run as ONE 2-D image of signal rows (capi.cu rows_view): the 2-D kernel families against
-# the oracle and against the 1-D kernels (TNMF_NO_ROWS_VIEW=1), whole batches and minibatch slices
+# the oracle and against the 1-D kernels (rows_view=False), whole batches and minibatch slices
 # ---------------------------------------------------------------------------------------------------------
 ROWS_CASES = [
     # N, M, D, A
@@ -299,15 +299,14 @@ ROWS_CASES = [
 
 @pytest.mark.parametrize('mode', ('valid', 'full'))
 @pytest.mark.parametrize('case', range(len(ROWS_CASES)))
-def test_rows_view_1d_vs_oracle(case, mode, monkeypatch):
+def test_rows_view_1d_vs_oracle(case, mode):
     N, M, D, A = ROWS_CASES[case]
-    monkeypatch.setenv('TNMF_ROWS_VIEW_MIN', '0')       # 'auto' takes the view from 2^20 signal elements on
     rng = np.random.default_rng(700 + case)
     V = rng.random((N, 1, D)).astype(np.float32)
     W = rng.random((M, 1, A)).astype(np.float32)
     H = rng.random((N, M) + orc.transform_shape(mode, (D,), (A,))).astype(np.float32)
     V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
-    be, Wd, Hd = _backend(V, W, H, mode)
+    be, Wd, Hd = _backend(V, W, H, mode, rows_view=True)    # 'auto' takes the view from 2^20 signal elements on
     assert Hd.stride(1) % 4 == 0 and Hd.stride(0) == M * Hd.stride(1)      # padded rows, [n, m, t] order kept
     tol = 2e-5
     for s in (slice(1, N - 1), slice(N - 1, N), slice(None)):
@@ -344,8 +343,7 @@ def test_rows_view_1d_vs_oracle(case, mode, monkeypatch):
     grad = torch.empty((2, *Wd.shape), dtype=Wd.dtype, device=Wd.device)
     be.apply_W_update(Wd, be.gradient_W(V, Wd, Hd, slice(None), grad))
     _close(Wd, nmf.W, 5e-5)
-    monkeypatch.setenv('TNMF_NO_ROWS_VIEW', '1')
-    be1, W1, H1 = _backend(V, W, H, mode)
+    be1, W1, H1 = _backend(V, W, H, mode, rows_view=False)
     for s in (slice(0, 1), slice(1, N)):
         be1.update_H(V, W1, H1, s, 0.1)
     be1.update_H(V, W1, H1, slice(None), 0.1, 0.2, 0.3, nmf.inhibition_kernels)
@@ -374,15 +372,14 @@ TMA_CASES = [
 
 @pytest.mark.parametrize('mode', ('valid', 'full'))
 @pytest.mark.parametrize('case', range(len(TMA_CASES)))
-def test_tma_vs_oracle(case, mode, monkeypatch):
-    monkeypatch.setenv('TNMF_NO_TC', '1')       # 'auto' without the tensor-core H update: this test pins the FP32 kernels
+def test_tma_vs_oracle(case, mode):
     N, C, M, D, A = TMA_CASES[case]
     rng = np.random.default_rng(200 + case)
     V = rng.random((N, C) + D).astype(np.float32)
     W = rng.random((M, C) + A).astype(np.float32)
     H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
     V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
-    be, Wd, Hd = _backend(V, W, H, mode, 'auto')
+    be, Wd, Hd = _backend(V, W, H, mode, 'auto', tensor_cores=False)   # 'auto' without tensor cores: pins the FP32 kernels
     tol = 2e-5
     R = orc.reconstruct(W64, H64, mode)
     _close(be.reconstruct(Wd, Hd), R, tol)

@@ -29,7 +29,10 @@ MODES = {'valid': 0, 'full': 1, 'circular': 2}
 PATHS = {'auto': 0, 'generic': 1, 'tiled': 2, 'tma': 3, 'tc': 4}
 OP_RECONSTRUCT, OP_GRADIENT_H, OP_GRADIENT_W = 0, 1, 2
 TNMF_OK, TNMF_EINVAL, TNMF_EUNSUPPORTED, TNMF_EWORKSPACE, TNMF_ECUDA = 0, 1, 2, 3, 1000
-ABI_VERSION = 3
+ABI_VERSION = 4
+# tnmf_problem.flags (include/tnmf_b200.h)
+FLAG_NO_ROWS_VIEW, FLAG_ROWS_VIEW_ALWAYS = 1, 2
+FLAG_NO_TC_HUPD, FLAG_NO_TC_RECON, FLAG_NO_TC_GRADW, FLAG_NO_TC, FLAG_NO_TMA = 4, 8, 16, 28, 32
 
 
 class Problem(ctypes.Structure):
@@ -40,6 +43,7 @@ class Problem(ctypes.Structure):
         ('h_pitch', ctypes.c_int32),
         ('sample_shape', ctypes.c_int32 * 3), ('atom_shape', ctypes.c_int32 * 3),
         ('h_stride_n', ctypes.c_int64), ('h_stride_m', ctypes.c_int64),
+        ('flags', ctypes.c_int32), ('reserved', ctypes.c_int32),
     ]
 
 
@@ -89,13 +93,22 @@ def build(force: bool = False, verbose: bool = False, jobs: Optional[int] = None
     units = [(s, s.replace('.cu', '.o'), []) for s in SOURCES]
     units += [(s, s.replace('.cu', f'_axc{c}.o'), [f'-DTNMF_AXC={c}']) for s in CHUNKED_SOURCES for c in CHUNKS]
     jobs = jobs or max(1, min(len(units), os.cpu_count() or 1))
-    pending = list(units)
-    running, objs, log = [], [], []
+    # incremental: a unit is recompiled when its object is older than its source, any header or this recipe
+    common = [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS] + [os.path.abspath(__file__)]
+    newest_common = max(os.path.getmtime(d) for d in common)
+    extra = os.environ.get('TNMF_NVCC_EXTRA', '')
+    stamp = os.path.join(objdir, 'flags.txt')
+    if force or not os.path.exists(stamp) or open(stamp).read() != extra:
+        newest_common = float('inf')
+    objs = [os.path.join(objdir, obj) for _, obj, _ in units]
+    pending = [u for u in units
+               if not os.path.exists(os.path.join(objdir, u[1]))
+               or os.path.getmtime(os.path.join(objdir, u[1])) < max(newest_common, os.path.getmtime(os.path.join(CSRC, u[0])))]
+    running, log = [], []
     while pending or running:
         while pending and len(running) < jobs:
             src, obj, defs = pending.pop(0)
             obj = os.path.join(objdir, obj)
-            objs.append(obj)
             cmd = [nvcc, *NVCC_FLAGS, *os.environ.get('TNMF_NVCC_EXTRA', '').split(), *defs, '-Xptxas', '-v', '-c', os.path.join(CSRC, src), '-o', obj]
             running.append((f'{src} {" ".join(defs)}',
                             subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -106,7 +119,9 @@ def build(force: bool = False, verbose: bool = False, jobs: Optional[int] = None
             for _, other in running:
                 other.kill()
             raise RuntimeError(f'nvcc failed on {name}:\n{out}')
-    with open(os.path.join(objdir, 'ptxas.log'), 'w') as f:
+    with open(stamp, 'w') as f:
+        f.write(extra)
+    with open(os.path.join(objdir, 'ptxas.log'), 'a' if not force else 'w') as f:
         f.write('\n'.join(log))
     if verbose:
         print('\n'.join(log))
@@ -154,7 +169,7 @@ def check(status: int, what: str = '') -> None:
 
 def make_problem(n_samples: int, n_channels: int, n_atoms: int, sample_shape: Sequence[int],
                  atom_shape: Sequence[int], dtype_code: int, mode: str = 'valid', path: str = 'auto',
-                 h_stride_n: int = 0, h_stride_m: int = 0, h_pitch: int = 0) -> Problem:
+                 h_stride_n: int = 0, h_stride_m: int = 0, h_pitch: int = 0, flags: int = 0) -> Problem:
     if mode not in MODES:
         raise ValueError(f'Unsupported reconstruction mode "{mode}". Please choose "valid", "full" or "circular".')
     if len(sample_shape) != len(atom_shape):
@@ -168,4 +183,5 @@ def make_problem(n_samples: int, n_channels: int, n_atoms: int, sample_shape: Se
         p.sample_shape[i] = int(d)
         p.atom_shape[i] = int(a)
     p.h_stride_n, p.h_stride_m, p.h_pitch = int(h_stride_n), int(h_stride_m), int(h_pitch)
+    p.flags, p.reserved = int(flags), 0
     return p

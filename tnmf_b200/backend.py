@@ -45,10 +45,18 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         tnmf/backends/_Backend.py:83-98 (bit-identical seeded initialisation); 'device' draws them with the
         device RNG (for problem sizes whose float64 host draw would not fit host memory).
     kernel_path : 'auto' | 'generic' | 'tiled' | 'tma' | 'tc'   (diagnostics; see include/tnmf_b200.h)
+    tensor_cores : True (default) | False | subset of ('reconstruct', 'update_h', 'gradient_w')
+        which operations 'auto' may put on the tcgen05 kernels (diagnostics: pins the FP32 kernels in tests)
+    rows_view : None (default: batches of >= 2^20 signal elements) | True | False
+        run single-channel 1-D batches as one 2-D image of signal rows
+    tma : bool, default True; False keeps 'auto' off the TMA family
+    All three travel to the library in `tnmf_problem.flags`; nothing is read from the environment.
     """
 
+    _TC_FLAGS = {'update_h': _lib.FLAG_NO_TC_HUPD, 'reconstruct': _lib.FLAG_NO_TC_RECON, 'gradient_w': _lib.FLAG_NO_TC_GRADW}
+
     def __init__(self, reconstruction_mode: str = 'valid', device=None, init: str = 'numpy',
-                 kernel_path: str = 'auto'):
+                 kernel_path: str = 'auto', tensor_cores=True, rows_view: Optional[bool] = None, tma: bool = True):
         super().__init__(reconstruction_mode=reconstruction_mode)
         if reconstruction_mode in ('reflect', 'same'):
             raise NotImplementedError(f'reconstruction mode "{reconstruction_mode}" is not provided by the b200 backend')
@@ -65,13 +73,24 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device())
         self._init = init
         self._path = kernel_path
+        allowed = set(self._TC_FLAGS) if tensor_cores is True else set() if not tensor_cores else set(tensor_cores)
+        if not allowed <= set(self._TC_FLAGS):
+            raise ValueError('tensor_cores must be a bool or a subset of ' + ', '.join(self._TC_FLAGS))
+        self._flags = sum(f for op, f in self._TC_FLAGS.items() if op not in allowed)
+        if rows_view is not None:
+            self._flags |= _lib.FLAG_ROWS_VIEW_ALWAYS if rows_view else _lib.FLAG_NO_ROWS_VIEW
+        if not tma:
+            self._flags |= _lib.FLAG_NO_TMA
         self.n_atoms = None
         self._dtype = None
         self._V_src = None      # the object the caller passes as V ...
         self._V_dev = None      # ... and its device copy
         self._R_buf = None
         self._H_store = None
+        self._V_store = None
+        self._W_store = None
         self._ws = None
+        self.buffers_epoch = 0  # bumped whenever one of the buffers above is replaced (captured CUDA graphs watch it)
         self._energy_buf = None
         self._problems = {}
         self._taps = {}
@@ -106,6 +125,24 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             t = t.to(self.device, non_blocking=True)
         return t.contiguous()
 
+    def _upload_V(self, V_local) -> torch.Tensor:
+        """Device copy of the samples.  Host data lands in a buffer that is reused while the shape repeats (repeated
+        fits, streams): a stable address keeps captured CUDA graphs valid across fits and saves the allocation."""
+        if isinstance(V_local, torch.Tensor) and V_local.device == self.device:
+            return V_local.to(self._dtype).contiguous()
+        host = V_local if isinstance(V_local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(V_local))
+        buf = self._V_store
+        if buf is None or buf.shape != host.shape or buf.dtype != self._dtype:
+            buf = self._V_store = torch.empty(host.shape, dtype=self._dtype, device=self.device)
+        buf.copy_(host, non_blocking=True)
+        return buf
+
+    def _stored_W(self, w_shape) -> torch.Tensor:
+        buf = self._W_store
+        if buf is None or tuple(buf.shape) != tuple(w_shape) or buf.dtype != self._dtype:
+            buf = self._W_store = torch.empty(w_shape, dtype=self._dtype, device=self.device)
+        return buf
+
     def _device_V(self, V) -> torch.Tensor:
         """Device copy of V.  Like the reference's caching backends (tnmf/backends/NumPy.py:53,101,
         NumPy_CachingFFT.py:259,273) the copy made at `initialize` is reused while the same object is passed."""
@@ -122,7 +159,8 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         p = self._problems.get(key)
         if p is None:
             p = _lib.make_problem(n, self.n_channels, n_atoms, self._sample_shape, self.atom_shape,
-                                  _DTYPE_CODE[self._dtype], self._reconstruction_mode, self._path, hsn, hsm, pitch)
+                                  _DTYPE_CODE[self._dtype], self._reconstruction_mode, self._path, hsn, hsm, pitch,
+                                  self._flags)
             self._problems[key] = p
         return p
 
@@ -153,15 +191,20 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self._last_h_problem = p
         return p, H
 
-    def _alloc_H(self, shape, random: bool) -> torch.Tensor:
-        """Activation tensor of the reference's shape [n, M, *T].  For float32 problems with two shift axes (and
-        single-channel 1-D problems, which the library runs as one 2-D image of signal rows) the rows are padded to a
-        multiple of 4 elements (16 bytes) - the TMA kernels cut their boxes out of H and need that stride alignment -
-        and the returned tensor is the [..., :T_x] view of the padded buffer."""
+    def _h_padding(self, shape) -> int:
+        """Elements appended to every row of an activation tensor of this shape.  For float32 problems with two shift
+        axes (and single-channel 1-D problems, which the library may run as one 2-D image of signal rows) the rows are
+        padded to a multiple of 4 elements (16 bytes): the TMA kernels cut their boxes out of H and need that stride."""
         pad = (-shape[-1]) % 4
         rows = len(self.atom_shape) == 1 and self.n_channels == 1 and self._reconstruction_mode != 'circular'
         if self._dtype != torch.float32 or not (len(self.atom_shape) == 2 or rows) or self._path == 'generic':
             pad = 0
+        return pad
+
+    def _alloc_H(self, shape, random: bool) -> torch.Tensor:
+        """Activation tensor of the reference's shape [n, M, *T]: the [..., :T_x] view of a buffer whose rows carry the
+        padding of `_h_padding`."""
+        pad = self._h_padding(shape)
         padded = (*shape[:-1], shape[-1] + pad)
         # the storage of the previous fit is reused when the shape repeats (fit_stream, repeated fits): a fresh
         # cudaMalloc of a multi-GB H costs tens of milliseconds
@@ -169,6 +212,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         if buf is None or tuple(buf.shape) != tuple(padded) or buf.dtype != self._dtype:
             self._H_store = None
             buf = self._H_store = torch.empty(padded, dtype=self._dtype, device=self.device)
+            self.buffers_epoch += 1
         if random:
             buf.uniform_().neg_().add_(1)       # 1 - U[0, 1), like tnmf/backends/_Backend.py:92
         return buf[..., :shape[-1]] if pad else buf
@@ -179,6 +223,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             need = p.ws_need = int(self._lib.tnmf_workspace_bytes(ctypes.byref(p)))
         if self._ws is None or self._ws.numel() < need:
             self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=self.device)
+            self.buffers_epoch += 1
         return self._ws, self._ws.numel()
 
     def _R_for(self, n: int) -> torch.Tensor:
@@ -186,13 +231,28 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         numel = int(np.prod(shape))
         if self._R_buf is None or self._R_buf.numel() < numel or self._R_buf.dtype != self._dtype:
             self._R_buf = torch.empty(max(numel, 1), dtype=self._dtype, device=self.device)
+            self.buffers_epoch += 1
         return self._R_buf[:numel].view(shape)
 
+    def buffer_tensors(self) -> tuple:
+        """The scratch buffers kernels of this backend write to (kept alive by whoever captured their addresses)."""
+        return tuple(t for t in (self._ws, self._R_buf, self._H_store) if t is not None)
+
+    def buffer_pointers(self) -> tuple:
+        return tuple(t.data_ptr() for t in self.buffer_tensors())
+
     def kernel_families(self, n: Optional[int] = None) -> dict:
-        """Which kernel family (generic / tiled / tma) serves each hot-path operation of the current problem."""
+        """Which kernel family (generic / tiled / tma / tc) serves each hot-path operation: of the last problem run, or
+        of a batch of `n` samples laid out the way `initialize` would (nothing is allocated)."""
         names = {v: k for k, v in _lib.PATHS.items()}
-        p, _ = self._h_problem(self._alloc_H((1 if n is None else n, self.n_atoms, *self._transform_shape), False)) \
-            if n is not None else (self._last_h_problem, None)
+        if n is None:
+            p = self._last_h_problem
+        else:
+            shape = (int(n), self.n_atoms, *self._transform_shape)
+            pad = self._h_padding(shape)
+            hsm = int(np.prod(shape[2:-1], dtype=np.int64)) * (shape[-1] + pad)
+            p = self._problem(int(n), self.n_atoms, self.n_atoms * hsm, hsm,
+                              (shape[-1] + pad) if pad and len(self.atom_shape) >= 2 else 0)
         return {op: names.get(int(self._lib.tnmf_kernel_family(ctypes.byref(p), code)), 'none')
                 for op, code in (('reconstruct', _lib.OP_RECONSTRUCT), ('update_h', _lib.OP_GRADIENT_H),
                                  ('gradient_w', _lib.OP_GRADIENT_W))}
@@ -241,7 +301,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self._set_dimensions(V_local, atom_shape)
         self.n_atoms = int(n_atoms)
         self._V_src, self._V_dev = None, None
-        self._V_src, self._V_dev = V, self._to_device(V_local, self._dtype)
+        self._V_src, self._V_dev = V, self._upload_V(V_local)
 
         h_shape = (hi - lo, self.n_atoms, *self._transform_shape)
         w_shape = (self.n_atoms, self.n_channels, *self.atom_shape)
@@ -254,12 +314,14 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             del h_host
             if W is None:
                 w_host = np.asarray(1 - np.random.rand(*w_shape), dtype=np_dtype)
-                W = self._to_device(w_host)
+                W = self._stored_W(w_shape)
+                W.copy_(torch.from_numpy(w_host))
                 self.normalize(W, axes_W_normalization)
         else:
             H = self._alloc_H(h_shape, random=True)
             if W is None:
-                W = 1 - torch.rand(w_shape, dtype=self._dtype, device=self.device)
+                W = self._stored_W(w_shape)
+                W.uniform_().neg_().add_(1)
                 self.normalize(W, axes_W_normalization)
         if not isinstance(W, torch.Tensor) or W.device != self.device:
             W = self._to_device(W, self._dtype)          # a W kept from a run of another backend

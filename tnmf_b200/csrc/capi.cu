@@ -15,16 +15,14 @@ namespace {
 // mix).  V[n,0,x], R[n,0,x] and W[m,0,a] are already laid out that way; H[n,m,t] becomes the image's activation with
 // the sample stride as its row stride.  The 2-D kernel families (TMA staging, persistent CTAs) then serve the 1-D
 // problems as well - cfg4 (2048 x 4096, 64 atoms x 128): 28.1 -> 23.1 ms per iteration on B200.  Offsets inside one
-// "image" are 32-bit in the tiled kernels, hence the size guard; TNMF_NO_ROWS_VIEW=1 keeps the 1-D kernels,
-// TNMF_ROWS_VIEW_MIN=<elements> moves the batch size from which the view is taken (default 2^20 signal elements).
+// "image" are 32-bit in the tiled kernels, hence the size guard; tnmf_problem.flags: TNMF_FLAG_NO_ROWS_VIEW keeps the 1-D
+// kernels, TNMF_FLAG_ROWS_VIEW_ALWAYS takes the view whatever the batch size (default: from 2^20 signal elements on).
 void rows_view(const tnmf_problem *p, Geo &g) {
     if (p->ndim != 1 || g.C != 1 || g.wrap || p->dtype != TNMF_F32 || g.N < 2) return;
     if ((long long)g.N * g.D[2] >= (1ll << 30) || (long long)g.N * g.T[2] >= (1ll << 30)) return;
-    if (getenv("TNMF_NO_ROWS_VIEW")) return;
+    if (p->flags & TNMF_FLAG_NO_ROWS_VIEW) return;
     // small batches do not fill the persistent 2-D kernels (cfg1, 100 x 1000: 0.079 against 0.060 ms per iteration)
-    const char *min_env = getenv("TNMF_ROWS_VIEW_MIN");
-    const long long min_elems = min_env ? atoll(min_env) : (1ll << 20);
-    if ((long long)g.N * g.D[2] < min_elems) return;
+    if (!(p->flags & TNMF_FLAG_ROWS_VIEW_ALWAYS) && (long long)g.N * g.D[2] < (1ll << 20)) return;
     g.D[1] = g.N; g.T[1] = g.N; g.A[1] = 1; g.off[1] = 0;
     g.hsy = g.hsn;
     g.hsn = g.hsn * g.N;
@@ -37,9 +35,10 @@ int make_geo(const tnmf_problem *p, Geo &g, bool allow_rows_view = true) {
     if (p->ndim < 1 || p->ndim > TNMF_MAX_SHIFT_DIMS) return TNMF_EUNSUPPORTED;
     if (p->dtype != TNMF_F32 && p->dtype != TNMF_F64) return TNMF_EUNSUPPORTED;
     if (p->mode != TNMF_VALID && p->mode != TNMF_FULL && p->mode != TNMF_CIRCULAR) return TNMF_EINVAL;
-    if (p->n_samples < 0 || p->n_channels < 1 || p->n_atoms < 1) return TNMF_EINVAL;
+    if (p->n_samples < 0 || p->n_channels < 1 || p->n_atoms < 1 || p->reserved != 0) return TNMF_EINVAL;
     g.N = p->n_samples; g.C = p->n_channels; g.M = p->n_atoms; g.ndim = p->ndim;
     g.wrap = p->mode == TNMF_CIRCULAR;
+    g.flags = p->flags;
     const int lead = 3 - p->ndim;
     for (int i = 0; i < 3; ++i) { g.D[i] = 1; g.A[i] = 1; g.T[i] = 1; g.off[i] = 0; }
     for (int i = 0; i < p->ndim; ++i) {
@@ -64,27 +63,27 @@ int make_geo(const tnmf_problem *p, Geo &g, bool allow_rows_view = true) {
 
 // The tensor-core H update pads the contraction C*A_x to a multiple of 8 and the atoms to a multiple of 16; 'auto'
 // takes it when at least half of every MMA is useful work and the problem fills the 128-column tiles
-// (TNMF_NO_TC=1 in the environment keeps 'auto' on the FP32 kernels).
+// (TNMF_FLAG_NO_TC_HUPD keeps 'auto' on the FP32 kernels).
 bool tc_worthwhile(const Geo &g) {
-    if (getenv("TNMF_NO_TC")) return false;
+    if (g.flags & TNMF_FLAG_NO_TC_HUPD) return false;
     const int k = g.C * g.A[2], kp = (k + 7) / 8 * 8, mp = (g.M + 15) / 16 * 16;
     const double useful = ((double)k / kp) * ((double)g.M / mp);
     return useful >= 0.5 && (long long)g.N * g.T[2] >= 128 && g.A[1] >= 3;
 }
 
 // The tensor-core reconstruction has N = roundup(A_y * C, 16) <= 64: every MMA sits on the per-instruction floor, so it
-// pays when many (atom row, channel) pairs share one MMA and the atoms fill the K steps (TNMF_NO_TC_RECON=1 keeps FP32).
+// pays when many (atom row, channel) pairs share one MMA and the atoms fill the K steps (TNMF_FLAG_NO_TC_RECON keeps FP32).
 bool tc_recon_worthwhile(const Geo &g) {
-    if (getenv("TNMF_NO_TC") || getenv("TNMF_NO_TC_RECON")) return false;
+    if (g.flags & TNMF_FLAG_NO_TC_RECON) return false;
     const int km = (g.M + 7) / 8 * 8;
     return g.A[1] * g.C >= 24 && (double)g.M / km >= 0.75 && (long long)g.N * g.D[2] >= 128;
 }
 
 // The tensor-core W gradient stacks the expanded V and R rows (of two consecutive source rows when the atom is narrow)
 // into the 128 MMA lanes: 2 * S * roundup(C*A_x, 8) of them carry taps.  'auto' takes it when that is at least half of
-// the tile (TNMF_NO_TC_GRADW=1 keeps the FP32 kernel).
+// the tile (TNMF_FLAG_NO_TC_GRADW keeps the FP32 kernel).
 bool tc_gradw_worthwhile(const Geo &g) {
-    if (getenv("TNMF_NO_TC") || getenv("TNMF_NO_TC_GRADW")) return false;
+    if (g.flags & TNMF_FLAG_NO_TC_GRADW) return false;
     const int kp = (g.C * g.A[2] + 7) / 8 * 8, mp = (g.M + 15) / 16 * 16;
     const int stack = (4 * kp <= 128 && 16 * (g.A[1] + 1) <= 256) ? 2 : 1;
     // atoms higher than 15 rows run in row chunks that expand V and R once per chunk: measured no faster than the FP32

@@ -28,6 +28,7 @@ struct Geo {
     int ndim;
     long long hsn, hsm;   // element strides of H's leading axes
     long long hsy;        // element stride between rows of H (>= T[2]; the last axis is always dense)
+    int flags;            // tnmf_problem.flags (TNMF_FLAG_*)
 };
 
 __host__ __device__ inline long long vol3(const int *s) { return (long long)s[0] * s[1] * s[2]; }

@@ -295,8 +295,8 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
 #pragma unroll
                 for (int ml = 0; ml < kNB; ++ml) hv[ml] = hnext[ml];
                 if (fast) {
-                    // plain fused update of a full block of 16 atoms: pointer walks, no per-atom tests.  The quotient
-                    // uses the reciprocal unit (2 ulp): its error is below that of the 3xTF32 products it divides.
+                    // plain fused update of a full block of 16 atoms: pointer walks, no per-atom tests.  The product and the
+                    // quotient round separately and to nearest, like the reference's `arr *= neg; arr /= pos`.
                     if (active) {
                         float *o = hrow + (long long)ty * g.hsy;
                         if (ty + 1 < w.ty1) {
@@ -306,7 +306,7 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
                         }
 #pragma unroll
                         for (int ml = 0; ml < kNB; ++ml) {
-                            *o = __fdividef(hv[ml] * neg[ml], pos[ml] + a.reg);
+                            *o = __fdiv_rn(__fmul_rn(hv[ml], neg[ml]), __fadd_rn(pos[ml], a.reg));
                             o += g.hsm;
                         }
                     }

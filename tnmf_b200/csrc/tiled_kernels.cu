@@ -78,8 +78,7 @@ bool make_hupd_plan(const Geo2 &g, TilePlan &p) {
     p = TilePlan();
     p.ch = choose_chunk(g.AX);
     const bool one_d = g.TY == 1 && g.AY == 1;
-    int mb_max = 4;
-    if (const char *e = getenv("TNMF_HUPD_MB")) mb_max = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 4;
+    const int mb_max = 4;
     const int nmb = ceil_div(g.M, mb_max);
     p.NB = ceil_div(g.M, nmb);
     p.nblk = nmb;

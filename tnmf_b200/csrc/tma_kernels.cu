@@ -79,9 +79,7 @@ static bool finish_tile_plan(Plan &p, int EY, int EX_in, int AY, int RB, int pla
     const int AXP = p.ch.AXP;
     const int wtile_y = kLY * RB, wtile_x = kLX * kCols;
     const int need_wy = ceil_div(EY, wtile_y), need_wx = ceil_div(EX, wtile_x);
-    int force_wx = 0, force_wy = 0;
-    if (const char *e = getenv("TNMF_TMA_WX")) force_wx = atoi(e);
-    if (const char *e = getenv("TNMF_TMA_WY")) force_wy = atoi(e);
+    const int force_wx = 0, force_wy = 0;      // tuning hook: a forced warp grid
     double best_cost = -1;
     Plan best = p;
     for (int wx = 1; wx <= max_consumers && wx <= need_wx; ++wx) {
@@ -294,7 +292,7 @@ static bool tma_geometry_ok(const Geo &g, int dtype) {
     if (dtype != TNMF_F32 || g.wrap) return false;
     if (g.D[0] != 1 || g.A[0] != 1 || g.T[0] != 1) return false;      // rank <= 2
     if (g.D[1] == 1 && g.A[1] == 1) return false;                     // rank 1: the cp.async kernels serve it
-    if (getenv("TNMF_NO_TMA")) return false;
+    if (g.flags & TNMF_FLAG_NO_TMA) return false;
     return g.N >= 1;
 }
 

@@ -56,6 +56,11 @@ class SampleSharding:
     def is_sharded(self) -> bool:
         return self.enabled and self.world_size > 1
 
+    @property
+    def capturable(self) -> bool:
+        """Whether the collectives can be recorded into a CUDA graph (NCCL can, gloo cannot)."""
+        return self.enabled and 'nccl' in str(dist.get_backend(self.group)).lower()
+
     def bounds(self, n_samples: int) -> Tuple[int, int]:
         return shard_bounds(n_samples, self.world_size, self.rank)
 

@@ -47,6 +47,9 @@ class TransformInvariantNMF:
     input_is_local_shard : bool, default False
         False: every rank passes the same global V and keeps its contiguous block of samples.
         True: every rank passes only its own samples.
+    equal_shards : bool, default False
+        With `input_is_local_shard`: the caller guarantees that all ranks pass equally many samples on every fit
+        (checked once per shape), which removes the per-fit exchange of the sample counts.
     fused : bool, default True
         False drives the backend through the reference interface only (reconstruction_gradient_H/W + the
         update arithmetic as tensor operations), i.e. exactly the call sequence of the stock facade.
@@ -60,7 +63,7 @@ class TransformInvariantNMF:
     def __init__(self, n_atoms: int, atom_shape: Tuple[int, ...], inhibition_range: Union[int, Tuple[int, ...]] = None,
                  backend: str = 'b200', logger: logging.Logger = None, verbose: int = 0,
                  distributed: Optional[bool] = None, process_group=None, input_is_local_shard: bool = False,
-                 fused: bool = True, cuda_graph: bool = True, **kwargs):
+                 fused: bool = True, cuda_graph: bool = True, equal_shards: bool = False, **kwargs):
         self.atom_shape = tuple(atom_shape)
         if inhibition_range is None:
             self._inhibition_range = tuple(a - 1 for a in self.atom_shape)   # just covers the atom
@@ -86,6 +89,9 @@ class TransformInvariantNMF:
         self._cuda_graph = bool(cuda_graph)
         self._sharding = SampleSharding(process_group, distributed)
         self._input_is_local = bool(input_is_local_shard)
+        self._equal_shards = bool(equal_shards)
+        self._counts_for = None
+        self._step_cache = None     # (key, _GraphedStep): CUDA graphs survive across fits while every buffer stays put
 
         self._logger = logger if logger is not None else logging.getLogger(self.__class__.__name__)
         self._logger.setLevel([logging.ERROR, logging.WARNING, logging.INFO, logging.DEBUG][verbose])
@@ -220,23 +226,32 @@ class TransformInvariantNMF:
             sample_range = sh.bounds(V.shape[0])
             self._n_global = int(V.shape[0])
             self._n_local_max = sh.max_local(V.shape[0])
+        elif sh.is_sharded:
+            # every rank passes its own samples: the global count and the largest shard need one exchange.  It is
+            # cached while the caller promises equal shards (`equal_shards=True`: streams of equally sized subsamples)
+            # - the two collectives and their host read-back are the only host synchronisation of a fit.
+            if not (self._equal_shards and self._counts_for == int(V.shape[0])):
+                counts = torch.tensor([V.shape[0], -V.shape[0]], dtype=torch.int64, device=self._backend.device)
+                torch.distributed.all_reduce(counts, op=torch.distributed.ReduceOp.MAX, group=sh.group)
+                n_max, n_min = int(counts[0].item()), -int(counts[1].item())
+                if self._equal_shards and n_max != n_min:
+                    raise ValueError(f'equal_shards=True, but the ranks hold between {n_min} and {n_max} samples')
+                n = torch.tensor([V.shape[0]], dtype=torch.int64, device=self._backend.device)
+                sh.sum_scalar(n)
+                self._n_global, self._n_local_max = int(n.item()), n_max
+                self._counts_for = int(V.shape[0])
         else:
             self._n_global = int(V.shape[0])
             self._n_local_max = int(V.shape[0])
-            if sh.is_sharded:
-                n = torch.tensor([V.shape[0]], dtype=torch.int64, device=self._backend.device)
-                n_max = n.clone()
-                torch.distributed.all_reduce(n_max, op=torch.distributed.ReduceOp.MAX, group=sh.group)
-                sh.sum_scalar(n)
-                self._n_global, self._n_local_max = int(n.item()), int(n_max.item())
         fresh_W = not (keep_W and self._W is not None)
         self._W, self._H = self._backend.initialize(V, self.atom_shape, self.n_atoms, None if fresh_W else self._W,
                                                     self._axes_W_normalization, sample_range=sample_range)
         if sample_range is not None:
             self._V = V[sample_range[0]:sample_range[1]]
             self._backend._V_src = self._V          # pylint: disable=protected-access
-        if fresh_W and sh.is_sharded and (self._input_is_local or self._backend._init == 'device'):  # pylint: disable=protected-access
-            sh.broadcast(self._W, 0)                # every rank must start from the same dictionary
+        if fresh_W and sh.is_sharded:
+            # every rank must start from the same dictionary, whatever the state of its random generator
+            sh.broadcast(self._W, 0)
         if self._grad is None or self._grad.shape[1:] != self._W.shape or self._grad.dtype != self._W.dtype:
             self._grad = torch.empty((2, *self._W.shape), dtype=self._W.dtype, device=self._W.device)
 
@@ -287,7 +302,12 @@ class TransformInvariantNMF:
                 reduce()
                 back()
             return eager
-        return _GraphedStep(self._backend, front, reduce, back, self._sharding.is_sharded)
+        if self._step_cache is None:
+            self._step_cache = {}
+        key = (bool(update_H), bool(update_W), float(sparsity), float(inhibition), float(cross_inhibition),
+               tuple(self._H.shape), tuple(self._H.stride()))
+        return _GraphedStep(self._backend, front, reduce, back, self._sharding, self._step_cache, key,
+                            (self._H, self._backend._device_V(self._V), self._W, self._grad))   # pylint: disable=protected-access
 
     # ---------------------------------------------------------------------------------------------
     # minibatch algorithms (tnmf/TransformInvariantNMF.py:350-504)
@@ -368,8 +388,18 @@ class TransformInvariantNMF:
         The next subsample is staged in pinned host memory and copied to the device on a side stream while the
         current one is being fitted."""
         feeder = _SubsampleFeeder(V, subsample_size, self._backend.device)
+        sh = self._sharding
         for isub in count(0):
             subsample = feeder.next()
+            if sh.is_sharded and self._input_is_local and not self._equal_shards:
+                # every fit issues collectives: ranks whose streams differ in length must stop together, or the
+                # longer ones would wait in the all-reduce for ever.  (`equal_shards=True` promises equal streams.)
+                have = torch.tensor([0 if subsample is None else 1], dtype=torch.int32, device=self._backend.device)
+                torch.distributed.all_reduce(have, op=torch.distributed.ReduceOp.MIN, group=sh.group)
+                if int(have.item()) == 0:
+                    if subsample is not None:
+                        self._logger.warning("Another rank's sample iterator is exhausted: stopping with samples left.")
+                    subsample = None
             if subsample is None:
                 self._logger.info("Sample iterator exhausted. TNMF on full iterator finished.")
                 return
@@ -394,15 +424,20 @@ class TransformInvariantNMF:
 
 class _GraphedStep:
     """One batch iteration = front (H update, local W gradient) -> all-reduce -> back (W update).  Call 1 runs eagerly
-    (it sizes the workspace and the reconstruction buffer), call 2 captures `front` and `back` into CUDA graphs - one
-    graph when there is no collective between them - and every call from then on replays them.  All buffers the kernels
-    touch are allocated before the capture and owned by the facade / backend for the life of the fit."""
+    (it sizes the workspace and the reconstruction buffer); call 2 captures the iteration into a CUDA graph - ONE graph,
+    the NCCL all-reduce included, so a multi-GPU step is a single launch with no host work between the W gradient and
+    the W update (with a process group that cannot be captured, gloo, the all-reduce stays an eager call between two
+    graphs) - and every call from then on replays it.  Captured graphs hold raw pointers: the step keeps every buffer the
+    kernels touch alive, re-captures when the backend had to replace one (`B200_Backend.buffers_epoch`), and the
+    facade caches the graphs across fits for as long as all pointers repeat (`cache`)."""
 
-    def __init__(self, backend, front, reduce, back, sharded: bool):
-        self._backend, self._front, self._reduce, self._back, self._sharded = backend, front, reduce, back, sharded
+    def __init__(self, backend, front, reduce, back, sharding, cache: dict, key: tuple, tensors: tuple):
+        self._backend, self._front, self._reduce, self._back = backend, front, reduce, back
+        self._sharded = sharding.is_sharded
+        self._one_graph = not self._sharded or sharding.capturable
         self._calls = 0
-        self._graphs = None
-        self._launches = 0
+        self._cache, self._key, self._tensors = cache, key, tensors
+        self._entry = None          # (graphs, launches per replay, buffers epoch, tensors kept alive)
 
     def _capture(self, fn):
         # capture_begin / capture_end on a side stream instead of the `torch.cuda.graph` context manager: the latter
@@ -419,28 +454,51 @@ class _GraphedStep:
             finally:
                 g.capture_end()
         torch.cuda.current_stream(dev).wait_stream(side)
-        self._launches += self._backend.launches - before
+        launches = self._backend.launches - before
         self._backend.launches = before
-        return g
+        return g, launches
+
+    def _full_key(self):
+        be = self._backend
+        return self._key + tuple(t.data_ptr() for t in self._tensors) + be.buffer_pointers()
+
+    def _eager(self):
+        self._front()
+        self._reduce()
+        self._back()
 
     def __call__(self):
         self._calls += 1
-        if self._calls == 1 or self._backend.kernel_events is not None:     # per-kernel timing needs eager launches
-            self._front()
-            self._reduce()
-            self._back()
+        be = self._backend
+        if self._calls == 1 or be.kernel_events is not None:        # per-kernel timing needs eager launches
+            self._eager()
             return
-        if self._graphs is None:
-            torch.cuda.current_stream(self._backend.device).synchronize()
-            if self._sharded:
-                self._graphs = (self._capture(self._front), self._capture(self._back))
-            else:
-                self._graphs = (self._capture(lambda: (self._front(), self._back())),)
-        self._graphs[0].replay()
-        if self._sharded:
+        if self._entry is not None and self._entry[2] != be.buffers_epoch:
+            self._cache.pop(self._entry[4], None)                   # a buffer moved under the captured pointers
+            self._entry = None
+            self._eager()
+            return
+        if self._entry is None:
+            key = self._full_key()
+            self._entry = self._cache.get(key)
+            if self._entry is None or self._entry[2] != be.buffers_epoch:
+                torch.cuda.current_stream(be.device).synchronize()
+                if self._one_graph:
+                    g, n = self._capture(self._eager)
+                    graphs = (g,)
+                else:
+                    (g0, n0), (g1, n1) = self._capture(self._front), self._capture(self._back)
+                    graphs, n = (g0, g1), n0 + n1
+                while len(self._cache) >= 4:
+                    self._cache.pop(next(iter(self._cache)))
+                self._entry = (graphs, n, be.buffers_epoch, self._tensors + be.buffer_tensors(), key)
+                self._cache[key] = self._entry
+        graphs = self._entry[0]
+        graphs[0].replay()
+        if len(graphs) > 1:
             self._reduce()
-            self._graphs[1].replay()
-        self._backend.launches += self._launches
+            graphs[1].replay()
+        be.launches += self._entry[1]
 
 
 class _SubsampleFeeder:
