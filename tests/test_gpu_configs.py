@@ -36,7 +36,7 @@ CONFIGS = {
     'cfg1': (100, 100, {}),
     'cfg2': (2, 100, {}),
     'cfg3': (4, 100, {}),
-    'cfg4': (8, 100, dict(rows_view=True)),    # bench: 2048 signals >= 2^20 elements take the rows view by themselves
+    'cfg4': (16, 100, dict(rows_view=True)),   # bench: 2048 signals >= 2^20 elements take the rows view by themselves
     'cfg5': (1, 20, {}),                       # 512 x 512, atoms 64 x 64: 20 iterations keep the oracle at seconds
 }
 TOL_E, TOL_W, TOL_H = 1e-4, 1e-3, 1e-3

@@ -84,6 +84,21 @@ __device__ __forceinline__ void mma_tf32_elect(unsigned tmem_d, unsigned long lo
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same with the A operand in TENSOR MEMORY (lane = operand row, 32-bit column = one K element; the column address must
+// be a multiple of 4).  Measured on B200 (tools/tc_probe2.cu): 128 x N x 8 takes N/2 clk from N = 48 on - no operand-fetch
+// floor (the shared-memory form needs >= 44 clk for its 4 KB A operand) and no A traffic on the shared-memory port.
+__device__ __forceinline__ void mma_tf32_ts_elect(unsigned tmem_d, unsigned tmem_a, unsigned long long desc_b, unsigned idesc,
+                                                  unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p, q;\n"
+        "elect.sync _|q, 0xffffffff;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit_elect(unsigned long long *bar) {
     asm volatile(
         "{\n"
@@ -130,6 +145,33 @@ __device__ __forceinline__ void tmem_ld16(unsigned addr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
+// 16 / 8 registers -> consecutive columns of this thread's TMEM lane (whole warp, lanes 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_st16(unsigned addr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::
+            "r"(addr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(unsigned addr, const float (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr),
+                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(unsigned addr) {
+    const unsigned z = 0u;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::
+            "r"(addr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 // x = hi + lo with hi the nearest TF32 (10-bit mantissa) and lo the remainder (the MMA truncates it to TF32).
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {

@@ -138,15 +138,6 @@ __device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan
     return w;
 }
 
-__device__ __forceinline__ void tmem_st16_zero(unsigned addr) {
-    const unsigned z = 0u;
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::
-            "r"(addr), "r"(z)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
-
 __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, const Plan p, const Args a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long a_full[kMaxStages], a_empty[kMaxStages], h_full[kRingMax], h_free[kRingMax], set_done[2],
