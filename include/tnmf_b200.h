@@ -65,6 +65,8 @@ extern "C" {
 #define TNMF_FLAG_NO_TC_GRADW     16   /* ... the W gradient */
 #define TNMF_FLAG_NO_TC           28   /* all three */
 #define TNMF_FLAG_NO_TMA          32   /* 'auto' skips the TMA family (cp.async tiled kernels instead) */
+#define TNMF_FLAG_NO_TMEM_OPERAND 64   /* tensor-core kernels keep their expanded operand in shared memory (the round-1
+                                        * kernels) instead of tensor memory */
 
 /* operations, for tnmf_kernel_family() */
 #define TNMF_OP_RECONSTRUCT 0

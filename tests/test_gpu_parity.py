@@ -429,9 +429,10 @@ TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize('tmem', (True, False))        # expanded operand in tensor memory / in shared memory (round-1 kernels)
 @pytest.mark.parametrize('mode', ('valid', 'full'))
 @pytest.mark.parametrize('case', range(len(TC_CASES)))
-def test_tc_hupdate_vs_oracle(case, mode):
+def test_tc_hupdate_vs_oracle(case, mode, tmem):
     """3xTF32 products carry ~2^-21 relative error against FP32's 2^-24: single operations within 2e-5 of max|ref|
     like the FP32 kernels, the fused update within 5e-5."""
     N, C, M, D, A = TC_CASES[case]
@@ -440,7 +441,7 @@ def test_tc_hupdate_vs_oracle(case, mode):
     W = rng.random((M, C) + A).astype(np.float32)
     H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
     V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
-    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc', tmem_operand=tmem)
     be.reconstruct(Wd, Hd)
     assert be.kernel_families()['update_h'] == 'tc'
     neg, pos = be.reconstruction_gradient_H(V, Wd, Hd)
@@ -461,9 +462,10 @@ def test_tc_hupdate_vs_oracle(case, mode):
     _close(Hd, nmf.H, 1e-4)
 
 
+@pytest.mark.parametrize('tmem', (True, False))        # expanded operand in tensor memory / in shared memory (round-1 kernels)
 @pytest.mark.parametrize('mode', ('valid', 'full'))
 @pytest.mark.parametrize('case', range(len(TC_CASES)))
-def test_tc_gradient_w_vs_oracle(case, mode):
+def test_tc_gradient_w_vs_oracle(case, mode, tmem):
     """Tensor-core W gradient (3xTF32, accumulator resident in TMEM, one partial slice per CTA) against the oracle;
     the sums run over all samples and positions, so the bound is relative to the largest entry."""
     N, C, M, D, A = TC_CASES[case]
@@ -472,7 +474,7 @@ def test_tc_gradient_w_vs_oracle(case, mode):
     W = rng.random((M, C) + A).astype(np.float32)
     H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
     V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
-    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc', tmem_operand=tmem)
     be.reconstruct(Wd, Hd)
     assert be.kernel_families()['gradient_w'] == 'tc'
     neg, pos = be.reconstruction_gradient_W(V, Wd, Hd)
@@ -535,9 +537,10 @@ def test_tc_gradient_w_tall_atoms_vs_oracle(case):
     assert be2.kernel_families()['gradient_w'] != 'tc'
 
 
+@pytest.mark.parametrize('tmem', (True, False))        # expanded operand in tensor memory / in shared memory (round-1 kernels)
 @pytest.mark.parametrize('mode', ('valid', 'full'))
 @pytest.mark.parametrize('case', range(len(TC_CASES)))
-def test_tc_reconstruct_vs_oracle(case, mode):
+def test_tc_reconstruct_vs_oracle(case, mode, tmem):
     """Tensor-core reconstruction (input-stationary, shifted-operand MMAs, register ring of output rows) and its fused
     energy against the oracle, plus the strided single-atom view of partial_reconstruct."""
     N, C, M, D, A = TC_CASES[case]
@@ -546,7 +549,7 @@ def test_tc_reconstruct_vs_oracle(case, mode):
     W = rng.random((M, C) + A).astype(np.float32)
     H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
     V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
-    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc', tmem_operand=tmem)
     R = be.reconstruct(Wd, Hd)
     assert be.kernel_families()['reconstruct'] == 'tc'
     ref = orc.reconstruct(W64, H64, mode)

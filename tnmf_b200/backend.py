@@ -50,13 +50,15 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
     rows_view : None (default: batches of >= 2^20 signal elements) | True | False
         run single-channel 1-D batches as one 2-D image of signal rows
     tma : bool, default True; False keeps 'auto' off the TMA family
-    All three travel to the library in `tnmf_problem.flags`; nothing is read from the environment.
+    tmem_operand : bool, default True; False keeps the tensor-core kernels on their shared-memory-operand form
+    All of them travel to the library in `tnmf_problem.flags`; nothing is read from the environment.
     """
 
     _TC_FLAGS = {'update_h': _lib.FLAG_NO_TC_HUPD, 'reconstruct': _lib.FLAG_NO_TC_RECON, 'gradient_w': _lib.FLAG_NO_TC_GRADW}
 
     def __init__(self, reconstruction_mode: str = 'valid', device=None, init: str = 'numpy',
-                 kernel_path: str = 'auto', tensor_cores=True, rows_view: Optional[bool] = None, tma: bool = True):
+                 kernel_path: str = 'auto', tensor_cores=True, rows_view: Optional[bool] = None, tma: bool = True,
+                 tmem_operand: bool = True):
         super().__init__(reconstruction_mode=reconstruction_mode)
         if reconstruction_mode in ('reflect', 'same'):
             raise NotImplementedError(f'reconstruction mode "{reconstruction_mode}" is not provided by the b200 backend')
@@ -81,6 +83,8 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             self._flags |= _lib.FLAG_ROWS_VIEW_ALWAYS if rows_view else _lib.FLAG_NO_ROWS_VIEW
         if not tma:
             self._flags |= _lib.FLAG_NO_TMA
+        if not tmem_operand:
+            self._flags |= _lib.FLAG_NO_TMEM_OPERAND
         self.n_atoms = None
         self._dtype = None
         self._V_src = None      # the object the caller passes as V ...

@@ -92,6 +92,11 @@ bool tc_gradw_worthwhile(const Geo &g) {
            g.A[1] >= 3 && g.A[1] <= 15;
 }
 
+// Tensor-core kernels whose expanded operand lives in tensor memory (tc_*_ts.cu) take over wherever they plan
+bool tmem_operand_gradw(const Geo &g, int dtype) {
+    return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_gradw_ts_supported(g, dtype);
+}
+
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;
 // a forced family that cannot serve the problem is an error.
 int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
@@ -104,7 +109,7 @@ int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
         tc_recon_supported(g, p->dtype))
         return TNMF_PATH_TC;
     if (op == TNMF_OP_GRADIENT_W && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_gradw_worthwhile(g))) &&
-        tc_gradw_supported(g, p->dtype))
+        (tc_gradw_supported(g, p->dtype) || tmem_operand_gradw(g, p->dtype)))
         return TNMF_PATH_TC;
     bool tma_ok = false;
     if (p->path == TNMF_PATH_AUTO || p->path == TNMF_PATH_TMA || p->path == TNMF_PATH_TC) {
@@ -170,6 +175,10 @@ static size_t workspace_bytes_of(const Geo &g, int dtype) {
         const size_t w = align256(tc_gradw_workspace_bytes(g));
         if (w > bytes) bytes = w;
     }
+    if (tc_gradw_ts_supported(g, dtype)) {
+        const size_t w = align256(tc_gradw_ts_workspace_bytes(g));
+        if (w > bytes) bytes = w;
+    }
     return bytes;
 }
 
@@ -203,7 +212,8 @@ int tnmf_launch_count(const tnmf_problem *p, int op) {
     int err;
     const int f = choose_family(p, g, op, &err);
     if (f < 0) return -1;
-    if (op == TNMF_OP_GRADIENT_W) return f == TNMF_PATH_TC ? tc_gradw_launches(g) : 2;      // + the finishing reduction
+    if (op == TNMF_OP_GRADIENT_W)                                                            // + the finishing reduction
+        return f != TNMF_PATH_TC ? 2 : tmem_operand_gradw(g, p->dtype) ? tc_gradw_ts_launches(g) : tc_gradw_launches(g);
     if (f == TNMF_PATH_TC) return op == TNMF_OP_RECONSTRUCT ? 1 : tc_hupd_launches(g);
     return f == TNMF_PATH_TMA ? 2 : 1;                                                      // + the atom pre-arrangement
 }
@@ -351,6 +361,9 @@ int tnmf_gradient_w(const tnmf_problem *p, const void *V, const void *R, const v
     if (s) return s;
     if (family == TNMF_PATH_TC) {
         if (!workspace || workspace_bytes < tnmf_workspace_bytes(p)) return TNMF_EWORKSPACE;
+        if (tmem_operand_gradw(g, p->dtype))
+            return tc_gradient_w_ts(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,
+                                    workspace, workspace_bytes, st);
         return tc_gradient_w(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,
                              workspace, workspace_bytes, st);
     }

@@ -1,0 +1,457 @@
+// Tensor-core (tcgen05, 3xTF32) W gradient with the expanded operand in TENSOR MEMORY.
+//
+//   neg[m,c,ay,ax] = sum_n sum_{ty,tx} H[n,m,ty,tx] * Vext[n,c,ty-offy+ay,tx-offx+ax]      (tnmf/backends/NumPy.py:77-85)
+//   pos[m,c,ay,ax] = the same with R                                                       (tnmf/backends/NumPy.py:80,87-90)
+//
+// Same product as tc_gradw.cu - a CTA owns 64 activation columns (column J = n * TXP + xv of the flattened [N x TXP] space,
+// TXP = TX + AX - 1) and walks down the source rows r; per row
+//       D'[k', (ay, m)] += sum_col A'[k', col] * B'[(ay, m), col],   k' = (X, c, ax), X in {V, R}
+//       A'[(X, c, ax), col] = Xext[n, c, r, xv - offx + ax]          B'[(slot, m), col] = H[n, m, ty(slot), xv]
+// with the activation rows B' in a shared-memory ring and the accumulator (lane = k', column = (ay, m)) resident in TMEM -
+// but A' never exists in shared memory: it is an operand in TENSOR MEMORY, lane = k', column = tile column.  The thread that
+// owns lane (X, c, ax) reads its shifted copy of the raw source row (conflict-free LDS.32: consecutive lanes, consecutive
+// words), splits hi/lo in registers and writes 16 columns with one tcgen05.st per half.  What that buys (measured,
+// tools/tc_probe2.cu and profiles/r02_*): the MMA no longer fetches a 4 KB A operand over the shared-memory port per
+// instruction (it was 45 % of the port's traffic), the expansion's STS.128 and its 70 % bank-conflict rate are gone, and the
+// operand lanes need no padding to 8-row core matrices.
+//
+// TMEM columns: two accumulator sets of NA = 16 * AY columns (a chain is cut after kEpoch source rows because the tensor
+// core truncates when it adds into the accumulator; while one set accumulates, the other is added into the CTA's slice in
+// global memory and zeroed), then the operand stages: KS columns of hi + KS of lo each (KS = 32 or 16 tile columns).
+// V taps sit in lanes [0, C*AX), R taps in lanes [64, 64 + C*AX), so all four lane quarters have writers.
+//
+// Roles (448 threads): warps 0-7 workers (warp w writes lane quarter w % 4, column half w / 4 of a stage; together they stage
+// the raw rows and the new activation row), warps 8 and 9 issue the MMAs of the two runs of the live-row window (fixed
+// accumulation order: bitwise reproducible), warps 10-13 drain the sets.  mbarriers: a_full/a_empty per operand stage,
+// h_full/h_free per ring slot, set_done/set_free per accumulator set.  Atoms in blocks of 16 (one launch per block).
+#include "tc_common.cuh"
+
+namespace tnmf {
+namespace tc {
+namespace gwt {
+
+using tiled::ceil_div;
+using tiled::Geo2;
+using tiled::round_up;
+
+constexpr int kCT = 64;             // activation columns per tile
+constexpr int kNB = 16;             // atoms per launch
+constexpr int kWorkers = 256;
+constexpr int kIssuers = 2;
+constexpr int kThreads = 32 * (8 + kIssuers + 4);
+constexpr int kEpoch = 8;           // source rows accumulated into one TMEM set before it is drained
+constexpr int kMaxAStages = 4;
+constexpr int kRingMax = 24;
+constexpr int kRawMax = 4;          // raw elements per worker: 2 * C * (64 + AX - 1) <= 1024
+constexpr int kMaxSmem = 226 * 1024;
+
+struct Plan {
+    int KPL;                        // taps per plane = C * AX (<= 64)
+    int TXP, RW, RWp, rawX, raw_floats, nraw;
+    int KS, n_sub, n_astages, a_col0, NA;
+    int RS, NRr, ring_floats;       // ring slots, ring rows (16 per slot), floats of ONE of the hi / lo halves
+    int tiles, rblocks, rows_per_block;
+    long long units;
+    int grid;
+    size_t smem;
+};
+
+struct Args {
+    const float *V, *R, *H;
+    float *partials;                // [grid][2][M*C*AY*AX]
+    int m0;
+};
+
+bool make_plan(const Geo2 &g, Plan &p) {
+    p = Plan();
+    if (g.AY < 1 || g.AY > 14) return false;
+    p.KPL = g.C * g.AX;
+    if (p.KPL > 64) return false;
+    p.NA = kNB * g.AY;
+    const int spare = 512 - 2 * p.NA;
+    if (spare >= 2 * 64) p.KS = 32;
+    else if (spare >= 2 * 32) p.KS = 16;
+    else return false;
+    p.n_sub = kCT / p.KS;
+    p.n_astages = spare / (2 * p.KS);
+    if (p.n_astages > kMaxAStages) p.n_astages = kMaxAStages;
+    p.a_col0 = 2 * p.NA;
+    p.TXP = g.TX + g.AX - 1;
+    p.RW = kCT + g.AX - 1;
+    // channel pitch == AX (mod 32): lane k = (c, ax) then reads word c * RWp + ax + col == k + col (mod 32): no bank conflicts
+    p.RWp = p.RW + 1;
+    while ((p.RWp - g.AX) % 32 != 0) ++p.RWp;
+    p.rawX = round_up(g.C * p.RWp, 32);
+    p.raw_floats = 2 * p.rawX + 128;                        // V plane, R plane, zeros for the idle lanes
+    p.nraw = ceil_div(2 * g.C * p.RW, kWorkers);
+    if (p.nraw > kRawMax) return false;
+    const size_t fixed = (size_t)2 * p.raw_floats * 4 + 1024;
+    for (p.RS = kRingMax; p.RS >= g.AY + 1; --p.RS) {
+        p.NRr = p.RS * kNB;
+        p.ring_floats = (p.NRr * 4 + 4) * (kCT / 4);        // K-chunk stride padded by 16 bytes: conflict-free row staging
+        if (fixed + (size_t)2 * p.ring_floats * 4 <= (size_t)kMaxSmem) break;
+    }
+    if (p.RS < g.AY + 1) return false;
+    p.smem = fixed + (size_t)2 * p.ring_floats * 4;
+    const long long cols = (long long)g.N * p.TXP;
+    if (cols <= 0 || cols >= (1ll << 31) - kCT) return false;
+    p.tiles = (int)((cols + kCT - 1) / kCT);
+    const int sms = tma::sm_count();
+    double best = -1;
+    for (int rb = 1; rb <= g.TY && rb <= 64; ++rb) {
+        const int rows = ceil_div(g.TY, rb);
+        if (ceil_div(g.TY, rows) != rb) continue;
+        const long long units = (long long)p.tiles * rb;
+        const double waves = (double)((units + sms - 1) / sms);
+        const double cost = waves * (rows + 0.5 * (g.AY - 1) + 1.0);
+        if (best < 0 || cost < best * 0.999) { best = cost; p.rblocks = rb; p.rows_per_block = rows; }
+    }
+    p.units = (long long)p.tiles * p.rblocks;
+    p.grid = (int)(p.units < sms ? p.units : sms);
+    return true;
+}
+
+struct Unit {
+    int tile, ty0, ty1, r_lo, r_hi;
+};
+__device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan &p) {
+    Unit w;
+    const int rb = (int)(u / p.tiles);
+    w.tile = (int)(u - (long long)rb * p.tiles);
+    w.ty0 = rb * p.rows_per_block;
+    w.ty1 = min(g.TY, w.ty0 + p.rows_per_block);
+    w.r_lo = max(0, w.ty0 - g.offy);
+    w.r_hi = min(g.DY - 1, w.ty1 - 1 - g.offy + g.AY - 1);
+    return w;
+}
+
+// KS: tile columns per operand stage (32: every worker thread writes 16 columns per half, 16: 8 columns)
+template <int KS>
+__global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, const Plan p, const Args a) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) unsigned long long a_full[kMaxAStages], a_empty[kMaxAStages], h_full[kRingMax], h_free[kRingMax],
+        set_done[2], set_free[2];
+    __shared__ unsigned tmem_base_s;
+    constexpr int CPT = KS / 2;                                  // columns per worker thread and stage
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int AY = g.AY, AX = g.AX, C = g.C, RS = p.RS, RW = p.RW;
+    float *ring_hi = smem, *ring_lo = smem + p.ring_floats;
+    float *raw = ring_lo + p.ring_floats;                       // [2 buffers][V plane | R plane | zeros]
+
+    if (tid == 0) {
+        for (int s = 0; s < p.n_astages; ++s) { mbar_init(&a_full[s], 8); mbar_init(&a_empty[s], kIssuers); }
+        for (int s = 0; s < kRingMax; ++s) { mbar_init(&h_full[s], kWorkers); mbar_init(&h_free[s], kIssuers); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&set_done[s], kIssuers); mbar_init(&set_free[s], 128); }
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc(&tmem_base_s, 512);
+    for (int idx = tid; idx < 2 * p.raw_floats; idx += kThreads) raw[idx] = 0.f;     // pads and the idle lanes' zeros
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = tmem_base_s;
+    if (warp < 4) {                                             // accumulators = 0, idle operand lanes = 0
+        for (int c = 0; c < 512; c += 16) tmem_st16_zero(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)c);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const long long count = (long long)g.M * C * AY * AX;
+
+    if (warp < 8) {
+        // ------------------------------------ workers ------------------------------------
+        const int quarter = warp & 3, half = warp >> 2;
+        const int L = quarter * 32 + lane;                      // operand lane of this thread
+        const int X = L >> 6, k = L & 63;
+        const bool live = k < p.KPL;
+        const bool warp_live = ((quarter * 32) & 63) < p.KPL;   // lane 0 of the warp carries a tap
+        const int src_off = live ? X * p.rawX + (k / AX) * p.RWp + (k % AX) : 2 * p.rawX;
+        const unsigned t_lane = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(p.a_col0 + half * CPT);
+        int st = 0;
+        unsigned ph = 0, buf = 0;
+        const long long plane = (long long)g.DY * g.DX;
+        const int raw_count = 2 * C * RW;
+        const int h_ml = tid >> 4, h_cg = tid & 15;             // activation chunk: atom ml, columns 4 cg .. 4 cg + 3
+        long long g_base = 0;
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit w = make_unit(u, g, p);
+            // source element of every raw slot (q = tid + 256 e -> tensor, channel, position) in row 0, or -1: zero
+            long long roff[kRawMax];
+            int rdst[kRawMax];
+#pragma unroll
+            for (int e = 0; e < kRawMax; ++e) {
+                roff[e] = -1;
+                rdst[e] = -1;
+                const int q = tid + kWorkers * e;
+                if (e < p.nraw && q < raw_count) {
+                    const int Xq = q / (C * RW), qq = q - Xq * (C * RW);
+                    const int c = qq / RW, xr = qq - c * RW;
+                    rdst[e] = Xq * p.rawX + c * p.RWp + xr;
+                    const long long J = (long long)w.tile * kCT + xr;
+                    const int n = (int)(J / p.TXP);
+                    const int x = (int)(J - (long long)n * p.TXP) - g.offx;
+                    if (n < g.N && (unsigned)x < (unsigned)g.DX) roff[e] = ((long long)n * C + c) * plane + x;
+                }
+            }
+            long long hoff[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const long long J = (long long)w.tile * kCT + 4 * h_cg + e;
+                const int n = (int)(J / p.TXP);
+                const int xv = (int)(J - (long long)n * p.TXP);
+                hoff[e] = (n < g.N && xv < g.TX && a.m0 + h_ml < g.M)
+                              ? (long long)n * g.hsn + (long long)(a.m0 + h_ml) * g.hsm + xv : -1;
+            }
+            float rv[kRawMax];
+            auto load_raw = [&](int r) {
+#pragma unroll
+                for (int e = 0; e < kRawMax; ++e) {
+                    const float *src = ((tid + kWorkers * e) >= C * RW) ? a.R : a.V;
+                    rv[e] = roff[e] >= 0 ? __ldg(src + (long long)r * g.DX + roff[e]) : 0.f;
+                }
+            };
+            auto load_h = [&](int ty) {
+                float4 hv;
+                hv.x = hoff[0] >= 0 ? a.H[hoff[0] + (long long)ty * g.hsy] : 0.f;
+                hv.y = hoff[1] >= 0 ? a.H[hoff[1] + (long long)ty * g.hsy] : 0.f;
+                hv.z = hoff[2] >= 0 ? a.H[hoff[2] + (long long)ty * g.hsy] : 0.f;
+                hv.w = hoff[3] >= 0 ? a.H[hoff[3] + (long long)ty * g.hsy] : 0.f;
+                return hv;
+            };
+            float4 hv_next = make_float4(0.f, 0.f, 0.f, 0.f);
+            int hv_row = -1;
+            int next_new = w.ty0;
+            load_raw(w.r_lo);
+            for (int r = w.r_lo; r <= w.r_hi; ++r) {
+                // ---- activation rows that enter the window with this source row ----
+                const int t_b = min(w.ty1 - 1, r + g.offy);
+                unsigned new_slots = 0;
+                for (; next_new <= t_b; ++next_new) {
+                    const long long gi = g_base + (next_new - w.ty0);
+                    const int slot = (int)(gi % RS);
+                    const float4 hv = next_new == hv_row ? hv_next : load_h(next_new);
+                    if (gi >= RS) mbar_wait_backoff(&h_free[slot], (unsigned)(((gi / RS) - 1) & 1), 40);
+                    float4 hi, lo;
+                    split_tf32(hv.x, hi.x, lo.x); split_tf32(hv.y, hi.y, lo.y);
+                    split_tf32(hv.z, hi.z, lo.z); split_tf32(hv.w, hi.w, lo.w);
+                    const int nrow = slot * kNB + h_ml;
+                    const size_t o = (size_t)(nrow >> 3) * 32 + (size_t)h_cg * (p.NRr * 4 + 4) + (size_t)(nrow & 7) * 4;
+                    *reinterpret_cast<float4 *>(ring_hi + o) = hi;
+                    *reinterpret_cast<float4 *>(ring_lo + o) = lo;
+                    new_slots |= 1u << slot;
+                }
+                if (new_slots) {
+                    fence_proxy_async();
+                    for (; new_slots; new_slots &= new_slots - 1) mbar_arrive(&h_full[__ffs(new_slots) - 1]);
+                }
+                // ---- raw V and R rows of this tile (plain FP32; split when they are expanded) ----
+                float *rb = raw + (size_t)buf * p.raw_floats;
+#pragma unroll
+                for (int e = 0; e < kRawMax; ++e)
+                    if (rdst[e] >= 0) rb[rdst[e]] = rv[e];
+                if (r < w.r_hi) load_raw(r + 1);                    // in flight while this row is expanded
+                if (next_new < w.ty1) { hv_next = load_h(next_new); hv_row = next_new; }
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                // ---- expansion into tensor memory: lane (X, c, ax) <- raw[X][c][ax + col] ----
+                const float *src = rb + src_off + half * CPT;
+                for (int h = 0; h < kCT / KS; ++h) {
+                    mbar_wait_backoff(&a_empty[st], ph ^ 1u, 20);
+                    tc_fence_after();
+                    if (warp_live) {
+                        float hi[CPT], lo[CPT];
+#pragma unroll
+                        for (int j = 0; j < CPT; ++j) split_tf32(src[h * KS + j], hi[j], lo[j]);
+                        const unsigned t = t_lane + (unsigned)(st * 2 * KS);
+                        if constexpr (CPT == 16) {
+                            tmem_st16(t, hi);
+                            tmem_st16(t + KS, lo);
+                        } else {
+                            tmem_st8(t, hi);
+                            tmem_st8(t + KS, lo);
+                        }
+                        tmem_st_wait();
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[st]);
+                    if (++st == p.n_astages) { st = 0; ph ^= 1u; }
+                }
+                buf ^= 1u;
+            }
+            g_base += w.ty1 - w.ty0;
+        }
+    } else if (warp >= 8 + kIssuers) {
+        // ------------------------------------ accumulator drainers ------------------------------------
+        long long rows_done = 0;
+        bool first_drain = true;
+        auto drain = [&](long long e) {
+            const int set = (int)(e & 1);
+            mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100);
+            tc_fence_after();
+            const int l = (warp & 3) * 32 + lane;
+            const int X = l >> 6, k = l & 63;
+            const bool live = k < p.KPL;
+            const int c = live ? k / AX : 0, ax = live ? k - c * AX : 0;
+            float *slice = a.partials + (long long)blockIdx.x * 2 * count + (long long)X * count;
+            const unsigned tbase = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(set * p.NA);
+            for (int j = 0; j < AY; ++j) {
+                float v[16];
+                tmem_ld16(tbase + (unsigned)(j * kNB), v);
+                tmem_ld_wait();
+                tmem_st16_zero(tbase + (unsigned)(j * kNB));
+                const int ay = AY - 1 - j;
+                if (live) {
+                    // all 16 running sums are fetched before the first store (stores would otherwise order the loads)
+                    float *dst0 = slice + (((long long)a.m0 * C + c) * AY + ay) * AX + ax;
+                    const long long mstride = (long long)C * AY * AX;
+                    float old[kNB];
+#pragma unroll
+                    for (int ml = 0; ml < kNB; ++ml)
+                        old[ml] = (!first_drain && a.m0 + ml < g.M) ? __ldcg(dst0 + ml * mstride) : 0.f;
+#pragma unroll
+                    for (int ml = 0; ml < kNB; ++ml)
+                        if (a.m0 + ml < g.M) __stcg(dst0 + ml * mstride, v[ml] + old[ml]);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&set_free[set]);
+            first_drain = false;
+        };
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit w = make_unit(u, g, p);
+            rows_done += w.r_hi - w.r_lo + 1;
+        }
+        const long long n_epochs = (rows_done + kEpoch - 1) / kEpoch;
+        for (long long e = 0; e < n_epochs; ++e) drain(e);
+    } else {
+        // ------------------------------------ MMA issuers (converged warps, one elected lane each) ------------------------------------
+        const unsigned lbo_b = (unsigned)p.NRr * 16 + 16;       // ring chunks carry a 16-byte pad
+        const unsigned desc_hi = (128u >> 4) | (1u << 14);      // SBO, descriptor version 1
+        const unsigned b_lo_word = ((lbo_b >> 4) << 16);
+        const unsigned ring16[3] = {smem_u32(ring_hi) >> 4, smem_u32(ring_hi) >> 4, smem_u32(ring_lo) >> 4};
+        const unsigned b_step16 = (2 * lbo_b) >> 4;
+        const int x = warp - 8;                 // warp 8 issues the first run of the live-row window, warp 9 the second
+        int st = 0;
+        unsigned ph = 0;
+        long long g_base = 0, rows_done = 0;
+        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
+            const Unit w = make_unit(u, g, p);
+            int next_new = w.ty0, next_out = w.ty0;
+            for (int r = w.r_lo; r <= w.r_hi; ++r) {
+                const long long epoch = rows_done / kEpoch;
+                if (rows_done % kEpoch == 0 && epoch >= 2) {
+                    mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1));
+                    tc_fence_after();
+                }
+                const unsigned tset = tmem_base + (unsigned)((epoch & 1) * p.NA);
+                const int ay_hi = min(AY - 1, r + g.offy - w.ty0);
+                const int t_a = r + g.offy - ay_hi, t_b = min(w.ty1 - 1, r + g.offy);
+                const int j0 = r + g.offy - AY + 1;                 // activation row of accumulator column block 0
+                for (; next_new <= t_b; ++next_new) {
+                    const long long gi = g_base + (next_new - w.ty0);
+                    mbar_wait(&h_full[gi % RS], (unsigned)((gi / RS) & 1));
+                }
+                // The window [t_a, t_b] is cut into two runs of ring slots, one per issuing warp: at the ring's wrap-around
+                // when it wraps, else in the middle.  Each warp issues ALL K steps of its run, so the runs accumulate into
+                // disjoint TMEM columns in a fixed order (bitwise reproducible whatever the interleaving of the warps).
+                unsigned o_col = 0, o_idesc = 0, o_b16 = 0;
+                bool have = false;
+                {
+                    const int cnt = t_b - t_a + 1;
+                    const int s0 = (int)((g_base + (t_a - w.ty0)) % RS);
+                    int first = min(cnt, RS - s0);                      // slots before the wrap-around
+                    if (first == cnt && cnt > 1) first = (cnt + 1) / 2;
+                    if (x == 0) {
+                        have = true;
+                        o_col = (unsigned)((t_a - j0) * kNB); o_idesc = idesc_tf32(128, kNB * first); o_b16 = (unsigned)s0 * 16u;
+                    } else if (cnt > first) {
+                        have = true;
+                        o_col = (unsigned)((t_a - j0 + first) * kNB); o_idesc = idesc_tf32(128, kNB * (cnt - first));
+                        o_b16 = (unsigned)((s0 + first) % RS) * 16u;
+                    }
+                }
+                for (int h = 0; h < kCT / KS; ++h) {
+                    mbar_wait(&a_full[st], ph);
+                    tc_fence_after();
+                    if (have) {
+                        const unsigned ta_hi = tmem_base + (unsigned)(p.a_col0 + st * 2 * KS), ta_lo = ta_hi + KS;
+#pragma unroll
+                        for (int ks = 0; ks < KS / 8; ++ks) {
+                            const unsigned kb = (unsigned)(h * (KS / 8) + ks) * b_step16 + o_b16;
+                            const unsigned long long b_hi = ((unsigned long long)desc_hi << 32) | (b_lo_word | (ring16[0] + kb));
+                            const unsigned long long b_lo = ((unsigned long long)desc_hi << 32) | (b_lo_word | (ring16[2] + kb));
+                            mma_tf32_ts_elect(tset + o_col, ta_hi + 8u * ks, b_hi, o_idesc, 1u);
+                            mma_tf32_ts_elect(tset + o_col, ta_lo + 8u * ks, b_hi, o_idesc, 1u);
+                            mma_tf32_ts_elect(tset + o_col, ta_hi + 8u * ks, b_lo, o_idesc, 1u);
+                        }
+                    }
+                    mma_commit_elect(&a_empty[st]);
+                    if (++st == p.n_astages) { st = 0; ph ^= 1u; }
+                }
+                // activation rows that leave the window: their slots may be overwritten once these MMAs are done
+                for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r; ++next_out)
+                    mma_commit_elect(&h_free[(g_base + (next_out - w.ty0)) % RS]);
+                if (++rows_done % kEpoch == 0) mma_commit_elect(&set_done[epoch & 1]);
+            }
+            g_base += w.ty1 - w.ty0;
+        }
+        if (rows_done % kEpoch != 0) mma_commit_elect(&set_done[(rows_done / kEpoch) & 1]);
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+template <int KS>
+static int launch(const Geo2 &g, const Plan &p, const Args &a, cudaStream_t st) {
+    auto kern = gradw_ts_kernel<KS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    kern<<<(unsigned)p.grid, kThreads, p.smem, st>>>(g, p, a);
+    TNMF_CHECK_LAUNCH();
+    return TNMF_OK;
+}
+
+}  // namespace gwt
+}  // namespace tc
+
+// ---- dispatch ----------------------------------------------------------------------------------------------------------
+bool tc_gradw_ts_supported(const Geo &g, int dtype) {
+    if (dtype != TNMF_F32 || g.wrap) return false;
+    if (g.D[0] != 1 || g.A[0] != 1 || g.T[0] != 1) return false;      // rank <= 2
+    if (g.D[1] == 1 && g.A[1] == 1) return false;                     // rank 1: the FP32 kernels serve it
+    if (g.N < 1) return false;
+    tc::gwt::Plan p;
+    return tc::gwt::make_plan(tiled::make_geo2(g), p);
+}
+
+size_t tc_gradw_ts_workspace_bytes(const Geo &g) {
+    tc::gwt::Plan p;
+    if (!tc::gwt::make_plan(tiled::make_geo2(g), p)) return 0;
+    return (size_t)p.grid * 2 * (size_t)g.M * g.C * g.A[1] * g.A[2] * sizeof(float);
+}
+
+int tc_gradient_w_ts(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
+                     size_t workspace_bytes, cudaStream_t st) {
+    const tiled::Geo2 q = tiled::make_geo2(g);
+    tc::gwt::Plan p;
+    if (!tc::gwt::make_plan(q, p)) return TNMF_EUNSUPPORTED;
+    const long long count = (long long)g.M * g.C * g.A[1] * g.A[2];
+    if (!workspace || workspace_bytes < tc_gradw_ts_workspace_bytes(g)) return TNMF_EWORKSPACE;
+    tc::gwt::Args a;
+    a.V = V; a.R = R; a.H = H; a.partials = (float *)workspace;
+    for (int m0 = 0; m0 < g.M; m0 += tc::gwt::kNB) {
+        a.m0 = m0;
+        const int s = p.KS == 32 ? tc::gwt::launch<32>(q, p, a, st) : tc::gwt::launch<16>(q, p, a, st);
+        if (s) return s;
+    }
+    return finish_gradient_w<float>((const float *)workspace, p.grid, count, neg, pos, st);
+}
+
+int tc_gradw_ts_launches(const Geo &g) { return tiled::ceil_div(g.M, tc::gwt::kNB) + 1; }
+
+}  // namespace tnmf
