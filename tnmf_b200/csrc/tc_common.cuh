@@ -99,6 +99,30 @@ __device__ __forceinline__ void mma_tf32_ts_elect(unsigned tmem_d, unsigned tmem
         "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// One lane of a converged warp (for `if (elect_one()) { several MMAs }`: the operands are moved to uniform registers once
+// per branch instead of once per instruction, as the per-instruction election of mma_tf32*_elect forces)
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long desc_b, unsigned idesc,
+                                            unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void mma_commit_elect(unsigned long long *bar) {
     asm volatile(
         "{\n"

@@ -20,9 +20,12 @@
 // global memory and zeroed), then the operand stages: KS columns of hi + KS of lo each (KS = 32 or 16 tile columns).
 // V taps sit in lanes [0, C*AX), R taps in lanes [64, 64 + C*AX), so all four lane quarters have writers.
 //
-// Roles (448 threads): warps 0-7 workers (warp w writes lane quarter w % 4, column half w / 4 of a stage; together they stage
-// the raw rows and the new activation row), warps 8 and 9 issue the MMAs of the two runs of the live-row window (fixed
-// accumulation order: bitwise reproducible), warps 10-13 drain the sets.  mbarriers: a_full/a_empty per operand stage,
+// Roles (416 threads): warps 0-7 workers (warp w writes lane quarter w % 4, column half w / 4 of a stage; together they stage
+// the raw rows and the new activation row), warp 8 issues the MMAs (a converged warp, one elected lane; the live-row window
+// is always one run of ring slots: the first AY - 1 slots are stored a second time behind the last one), warps 9-12 drain the sets.  One issuing warp keeps the
+// order of accumulation into every TMEM column fixed: with two warps taking one run each, a column changed hands between
+// source rows and the warps' relative progress decided which row was added first - run-to-run differences of one ulp
+// (found by tools/determinism_check.py; the tensor core truncates, so the order matters).  mbarriers: a_full/a_empty per operand stage,
 // h_full/h_free per ring slot, set_done/set_free per accumulator set.  Atoms in blocks of 16 (one launch per block).
 #include "tc_common.cuh"
 
@@ -37,7 +40,7 @@ using tiled::round_up;
 constexpr int kCT = 64;             // activation columns per tile
 constexpr int kNB = 16;             // atoms per launch
 constexpr int kWorkers = 256;
-constexpr int kIssuers = 2;
+constexpr int kIssuers = 1;         // ONE issuing warp: every accumulator column sees its MMAs in program order
 constexpr int kThreads = 32 * (8 + kIssuers + 4);
 constexpr int kEpoch = 8;           // source rows accumulated into one TMEM set before it is drained
 constexpr int kMaxAStages = 4;
@@ -49,7 +52,8 @@ struct Plan {
     int KPL;                        // taps per plane = C * AX (<= 64)
     int TXP, RW, RWp, rawX, raw_floats, nraw;
     int KS, n_sub, n_astages, a_col0, NA;
-    int RS, NRr, ring_floats;       // ring slots, ring rows (16 per slot), floats of ONE of the hi / lo halves
+    int RS, NRr, ring_floats;       // logical ring slots, physical ring rows (16 per slot, RS + AY - 1 slots: the first
+                                    // AY - 1 slots are mirrored behind the last one), floats of ONE of the hi / lo halves
     int tiles, rblocks, rows_per_block;
     long long units;
     int grid;
@@ -87,7 +91,7 @@ bool make_plan(const Geo2 &g, Plan &p) {
     if (p.nraw > kRawMax) return false;
     const size_t fixed = (size_t)2 * p.raw_floats * 4 + 1024;
     for (p.RS = kRingMax; p.RS >= g.AY + 1; --p.RS) {
-        p.NRr = p.RS * kNB;
+        p.NRr = (p.RS + g.AY - 1) * kNB;
         p.ring_floats = (p.NRr * 4 + 4) * (kCT / 4);        // K-chunk stride padded by 16 bytes: conflict-free row staging
         if (fixed + (size_t)2 * p.ring_floats * 4 <= (size_t)kMaxSmem) break;
     }
@@ -133,7 +137,9 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
         set_done[2], set_free[2];
     __shared__ unsigned tmem_base_s;
     constexpr int CPT = KS / 2;                                  // columns per worker thread and stage
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // the warp index comes out of a shuffle so that ptxas knows it is warp-uniform: the role branches below then are
+    // uniform branches and the code inside them may live in uniform registers (what the tcgen05 operands need)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int AY = g.AY, AX = g.AX, C = g.C, RS = p.RS, RW = p.RW;
     float *ring_hi = smem, *ring_lo = smem + p.ring_floats;
     float *raw = ring_lo + p.ring_floats;                       // [2 buffers][V plane | R plane | zeros]
@@ -167,14 +173,20 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
         const int X = L >> 6, k = L & 63;
         const bool live = k < p.KPL;
         const bool warp_live = ((quarter * 32) & 63) < p.KPL;   // lane 0 of the warp carries a tap
-        const int src_off = live ? X * p.rawX + (k / AX) * p.RWp + (k % AX) : 2 * p.rawX;
+        const int src_off = live ? X * p.rawX + (k / AX) * p.RWp + (k % AX) : 2 * p.rawX + 16;   // idle lanes: zeros, in the
+                                                                                              // bank a live lane 32 does not use
         const unsigned t_lane = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(p.a_col0 + half * CPT);
         int st = 0;
         unsigned ph = 0, buf = 0;
+        TC_PROF_DECL(empty); TC_PROF_DECL(hfree); TC_PROF_DECL(bar); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         const long long plane = (long long)g.DY * g.DX;
         const int raw_count = 2 * C * RW;
         const int h_ml = tid >> 4, h_cg = tid & 15;             // activation chunk: atom ml, columns 4 cg .. 4 cg + 3
-        long long g_base = 0;
+        int slot_new = 0;                                       // ring slot of the next activation row; no divisions in
+        unsigned wraps = 0;                                     // the row loop (they were most of its critical path)
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             // source element of every raw slot (q = tid + 256 e -> tensor, channel, position) in row 0, or -1: zero
@@ -229,10 +241,10 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
                 const int t_b = min(w.ty1 - 1, r + g.offy);
                 unsigned new_slots = 0;
                 for (; next_new <= t_b; ++next_new) {
-                    const long long gi = g_base + (next_new - w.ty0);
-                    const int slot = (int)(gi % RS);
+                    const int slot = slot_new;
                     const float4 hv = next_new == hv_row ? hv_next : load_h(next_new);
-                    if (gi >= RS) mbar_wait_backoff(&h_free[slot], (unsigned)(((gi / RS) - 1) & 1), 40);
+                    if (wraps) TC_PROF_WAIT(hfree, mbar_wait_backoff(&h_free[slot], (wraps - 1u) & 1u, 40));
+                    if (++slot_new == RS) { slot_new = 0; ++wraps; }
                     float4 hi, lo;
                     split_tf32(hv.x, hi.x, lo.x); split_tf32(hv.y, hi.y, lo.y);
                     split_tf32(hv.z, hi.z, lo.z); split_tf32(hv.w, hi.w, lo.w);
@@ -240,6 +252,11 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
                     const size_t o = (size_t)(nrow >> 3) * 32 + (size_t)h_cg * (p.NRr * 4 + 4) + (size_t)(nrow & 7) * 4;
                     *reinterpret_cast<float4 *>(ring_hi + o) = hi;
                     *reinterpret_cast<float4 *>(ring_lo + o) = lo;
+                    if (slot < AY - 1) {                                // mirror: a window never wraps (one MMA per K step)
+                        const size_t om = o + (size_t)RS * (kNB / 8) * 32;
+                        *reinterpret_cast<float4 *>(ring_hi + om) = hi;
+                        *reinterpret_cast<float4 *>(ring_lo + om) = lo;
+                    }
                     new_slots |= 1u << slot;
                 }
                 if (new_slots) {
@@ -253,11 +270,11 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
                     if (rdst[e] >= 0) rb[rdst[e]] = rv[e];
                 if (r < w.r_hi) load_raw(r + 1);                    // in flight while this row is expanded
                 if (next_new < w.ty1) { hv_next = load_h(next_new); hv_row = next_new; }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                TC_PROF_WAIT(bar, asm volatile("bar.sync 1, 256;\n" ::: "memory"));
                 // ---- expansion into tensor memory: lane (X, c, ax) <- raw[X][c][ax + col] ----
                 const float *src = rb + src_off + half * CPT;
                 for (int h = 0; h < kCT / KS; ++h) {
-                    mbar_wait_backoff(&a_empty[st], ph ^ 1u, 20);
+                    TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[st], ph ^ 1u, 20));
                     tc_fence_after();
                     if (warp_live) {
                         float hi[CPT], lo[CPT];
@@ -280,15 +297,24 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
                 }
                 buf ^= 1u;
             }
-            g_base += w.ty1 - w.ty0;
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && tid == 0)
+            printf("gradw_ts workers: total %lld  wait a_empty %lld  wait h_free %lld  raw barrier %lld\n", prof_total, prof_empty,
+                   prof_hfree, prof_bar);
+#endif
     } else if (warp >= 8 + kIssuers) {
         // ------------------------------------ accumulator drainers ------------------------------------
-        long long rows_done = 0;
+        int rows_done = 0;
         bool first_drain = true;
-        auto drain = [&](long long e) {
+        TC_PROF_DECL(done); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
+        auto drain = [&](int e) {
             const int set = (int)(e & 1);
-            mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100);
+            TC_PROF_WAIT(done, mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100));
             tc_fence_after();
             const int l = (warp & 3) * 32 + lane;
             const int X = l >> 6, k = l & 63;
@@ -324,81 +350,102 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
             const Unit w = make_unit(u, g, p);
             rows_done += w.r_hi - w.r_lo + 1;
         }
-        const long long n_epochs = (rows_done + kEpoch - 1) / kEpoch;
-        for (long long e = 0; e < n_epochs; ++e) drain(e);
+        const int n_epochs = (rows_done + kEpoch - 1) / kEpoch;
+        for (int e = 0; e < n_epochs; ++e) drain(e);
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && tid == 32 * (8 + kIssuers))
+            printf("gradw_ts drainers: total %lld  wait set_done %lld  (%d epochs)\n", prof_total, prof_done, n_epochs);
+#endif
     } else {
-        // ------------------------------------ MMA issuers (converged warps, one elected lane each) ------------------------------------
+        // ------------------------------------ MMA issuer (one converged warp, one elected lane) ------------------------------------
+        // everything an MMA names must sit in UNIFORM registers: a value ptxas cannot prove warp-uniform costs an R2UR per
+        // operand and instruction (35 instructions per MMA, measured: the issuing warp, not the tensor pipe, set the pace).
+        // A shuffle from lane 0 is the idiom that marks a loaded value as uniform.
+        const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const unsigned lbo_b = (unsigned)p.NRr * 16 + 16;       // ring chunks carry a 16-byte pad
         const unsigned desc_hi = (128u >> 4) | (1u << 14);      // SBO, descriptor version 1
         const unsigned b_lo_word = ((lbo_b >> 4) << 16);
-        const unsigned ring16[3] = {smem_u32(ring_hi) >> 4, smem_u32(ring_hi) >> 4, smem_u32(ring_lo) >> 4};
+        const unsigned ring_hi16 = __shfl_sync(0xffffffffu, smem_u32(ring_hi) >> 4, 0);
+        const unsigned ring_lo16 = __shfl_sync(0xffffffffu, smem_u32(ring_lo) >> 4, 0);
         const unsigned b_step16 = (2 * lbo_b) >> 4;
-        const int x = warp - 8;                 // warp 8 issues the first run of the live-row window, warp 9 the second
         int st = 0;
         unsigned ph = 0;
-        long long g_base = 0, rows_done = 0;
+        int rows_done = 0;
+        // ring bookkeeping without divisions: slot / wrap parity of the next row to enter, slot of the next row to leave,
+        // slot of the first row of the window
+        int slot_new = 0, slot_out = 0, slot_a = 0;
+        unsigned par_new = 0;
+        TC_PROF_DECL(full); TC_PROF_DECL(hfull); TC_PROF_DECL(setfree); TC_PROF_DECL(total); TC_PROF_DECL(issue);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
-            int next_new = w.ty0, next_out = w.ty0;
+            int next_new = w.ty0, next_out = w.ty0, win0 = w.ty0;
+            slot_a = slot_new;                                      // the unit's first activation row enters here
             for (int r = w.r_lo; r <= w.r_hi; ++r) {
-                const long long epoch = rows_done / kEpoch;
+                const int epoch = rows_done / kEpoch;
                 if (rows_done % kEpoch == 0 && epoch >= 2) {
-                    mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1));
+                    TC_PROF_WAIT(setfree, mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1)));
                     tc_fence_after();
                 }
-                const unsigned tset = tmem_base + (unsigned)((epoch & 1) * p.NA);
+                const unsigned tset = tmem_u + (unsigned)((epoch & 1) * p.NA);
                 const int ay_hi = min(AY - 1, r + g.offy - w.ty0);
                 const int t_a = r + g.offy - ay_hi, t_b = min(w.ty1 - 1, r + g.offy);
                 const int j0 = r + g.offy - AY + 1;                 // activation row of accumulator column block 0
                 for (; next_new <= t_b; ++next_new) {
-                    const long long gi = g_base + (next_new - w.ty0);
-                    mbar_wait(&h_full[gi % RS], (unsigned)((gi / RS) & 1));
+                    TC_PROF_WAIT(hfull, mbar_wait(&h_full[slot_new], par_new));
+                    if (++slot_new == RS) { slot_new = 0; par_new ^= 1u; }
                 }
-                // The window [t_a, t_b] is cut into two runs of ring slots, one per issuing warp: at the ring's wrap-around
-                // when it wraps, else in the middle.  Each warp issues ALL K steps of its run, so the runs accumulate into
-                // disjoint TMEM columns in a fixed order (bitwise reproducible whatever the interleaving of the warps).
-                unsigned o_col = 0, o_idesc = 0, o_b16 = 0;
-                bool have = false;
-                {
-                    const int cnt = t_b - t_a + 1;
-                    const int s0 = (int)((g_base + (t_a - w.ty0)) % RS);
-                    int first = min(cnt, RS - s0);                      // slots before the wrap-around
-                    if (first == cnt && cnt > 1) first = (cnt + 1) / 2;
-                    if (x == 0) {
-                        have = true;
-                        o_col = (unsigned)((t_a - j0) * kNB); o_idesc = idesc_tf32(128, kNB * first); o_b16 = (unsigned)s0 * 16u;
-                    } else if (cnt > first) {
-                        have = true;
-                        o_col = (unsigned)((t_a - j0 + first) * kNB); o_idesc = idesc_tf32(128, kNB * (cnt - first));
-                        o_b16 = (unsigned)((s0 + first) % RS) * 16u;
-                    }
-                }
+                for (; win0 < t_a; ++win0)
+                    if (++slot_a == RS) slot_a = 0;
+                // the window [t_a, t_b] is ONE run of physical ring slots (the head of the ring is mirrored behind its tail)
+                const int cnt = t_b - t_a + 1;
+                const int s0 = slot_a;
+                const unsigned col0 = tset + (unsigned)((t_a - j0) * kNB);
+                const unsigned idesc0 = idesc_tf32(128, kNB * cnt);
+                const unsigned b0 = (unsigned)s0 * 16u;
                 for (int h = 0; h < kCT / KS; ++h) {
-                    mbar_wait(&a_full[st], ph);
+                    TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
                     tc_fence_after();
-                    if (have) {
-                        const unsigned ta_hi = tmem_base + (unsigned)(p.a_col0 + st * 2 * KS), ta_lo = ta_hi + KS;
+                    const unsigned ta_hi = tmem_u + (unsigned)(p.a_col0 + st * 2 * KS), ta_lo = ta_hi + KS;
+#ifdef TNMF_TC_PROFILE
+                    const long long t_i = clock64();
+#endif
+                    if (elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < KS / 8; ++ks) {
-                            const unsigned kb = (unsigned)(h * (KS / 8) + ks) * b_step16 + o_b16;
-                            const unsigned long long b_hi = ((unsigned long long)desc_hi << 32) | (b_lo_word | (ring16[0] + kb));
-                            const unsigned long long b_lo = ((unsigned long long)desc_hi << 32) | (b_lo_word | (ring16[2] + kb));
-                            mma_tf32_ts_elect(tset + o_col, ta_hi + 8u * ks, b_hi, o_idesc, 1u);
-                            mma_tf32_ts_elect(tset + o_col, ta_lo + 8u * ks, b_hi, o_idesc, 1u);
-                            mma_tf32_ts_elect(tset + o_col, ta_hi + 8u * ks, b_lo, o_idesc, 1u);
+                            const unsigned kb = (unsigned)(h * (KS / 8) + ks) * b_step16 + b0;
+                            const unsigned long long b_hi = ((unsigned long long)desc_hi << 32) | (b_lo_word | (ring_hi16 + kb));
+                            const unsigned long long b_lo = ((unsigned long long)desc_hi << 32) | (b_lo_word | (ring_lo16 + kb));
+                            mma_tf32_ts(col0, ta_hi + 8u * ks, b_hi, idesc0, 1u);
+                            mma_tf32_ts(col0, ta_lo + 8u * ks, b_hi, idesc0, 1u);
+                            mma_tf32_ts(col0, ta_hi + 8u * ks, b_lo, idesc0, 1u);
                         }
                     }
+                    __syncwarp();
+#ifdef TNMF_TC_PROFILE
+                    prof_issue += clock64() - t_i;
+#endif
                     mma_commit_elect(&a_empty[st]);
                     if (++st == p.n_astages) { st = 0; ph ^= 1u; }
                 }
                 // activation rows that leave the window: their slots may be overwritten once these MMAs are done
-                for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r; ++next_out)
-                    mma_commit_elect(&h_free[(g_base + (next_out - w.ty0)) % RS]);
+                for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r; ++next_out) {
+                    mma_commit_elect(&h_free[slot_out]);
+                    if (++slot_out == RS) slot_out = 0;
+                }
                 if (++rows_done % kEpoch == 0) mma_commit_elect(&set_done[epoch & 1]);
             }
-            g_base += w.ty1 - w.ty0;
         }
         if (rows_done % kEpoch != 0) mma_commit_elect(&set_done[(rows_done / kEpoch) & 1]);
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && lane == 0)
+            printf("gradw_ts mma: total %lld  wait a_full %lld  wait h_full %lld  wait set_free %lld  issuing %lld (%d rows)\n",
+                   prof_total, prof_full, prof_hfull, prof_setfree, prof_issue, rows_done);
+#endif
         __syncwarp();
     }
     tc_fence_before();

@@ -12,40 +12,9 @@
 
 using namespace tnmf::tc;
 
-__device__ __forceinline__ void mma_tf32_ts(unsigned tmem_d, unsigned tmem_a, unsigned long long desc_b, unsigned idesc,
-                                            unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mma_tf32_ts_elect(unsigned tmem_d, unsigned tmem_a, unsigned long long desc_b, unsigned idesc,
-                                                  unsigned accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p, q;\n"
-        "elect.sync _|q, 0xffffffff;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st8(unsigned addr, const float (&v)[8]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(addr),
-                 "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-                 "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
-                 "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_st1(unsigned addr, float v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};\n" ::"r"(addr), "r"(__float_as_uint(v)) : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 // A: 128 x KP (row-major global), written to TMEM columns [acol, acol + KP) (hi) and [acol + KP, acol + 2 KP) (lo);
 // the MMA reads it from column acol + shift, i.e. it multiplies A[:, shift : shift + KP'] with KP' = KP - shift rounded
@@ -136,16 +105,17 @@ static double run_ts(int KP, int N, int acol, int shift) {
     return worst;
 }
 
-// Timing.  Warp 0 issues `count` MMAs (converged warp, elected lane) of 128 x N x 8 into ndst alternating TMEM ranges; A from
-// TMEM (ts = 1) or shared memory (ts = 0).  Warps 1..hammer each run a loop of conflict-free LDS.128 over 32 KB until the
-// issuer is done (hammer = 0: nobody).  Reports cycles per MMA.
+// Timing.  Warp 8 issues `count` MMAs of 128 x N x 8 (one elected lane, uniform operands) into ndst alternating TMEM ranges; A
+// from TMEM (ts = 1) or shared memory (ts = 0).  Warps 0..7 meanwhile generate the traffic named by `hammer` (bit 0: LDS.128,
+// bit 1: STS.128, bit 2: tcgen05.st x16, bit 3: tcgen05.ld x16 - the latter two on TMEM columns the MMAs do not touch) until
+// the issuer is done.  Reports cycles per MMA and the hammer rates.
 __global__ void __launch_bounds__(32 * 9, 1) time_kernel(long long *out, int N, int count, int ndst, int ts, int hammer,
                                                         float *sink) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long bar;
     __shared__ unsigned tmem_base_s;
     __shared__ volatile int done;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int KP = 16, NR = 256;
     for (int idx = tid; idx < (128 + NR) * KP + 8192; idx += blockDim.x) smem[idx] = 1.0f;
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); done = 0; }
@@ -154,7 +124,7 @@ __global__ void __launch_bounds__(32 * 9, 1) time_kernel(long long *out, int N, 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const unsigned tmem_base = tmem_base_s;
+    const unsigned tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
     if (warp < 4) {                                             // A in TMEM columns [448, 464): ones
         for (int c = 0; c < 16; ++c) tmem_st1(tmem_base + ((unsigned)(warp * 32) << 16) + 448u + c, 1.0f);
         tmem_st_wait();
@@ -162,7 +132,7 @@ __global__ void __launch_bounds__(32 * 9, 1) time_kernel(long long *out, int N, 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == 8) {                                            // the highest warp id wins the issue arbiter
+    if (warp == 8) {
         const unsigned lbo_a = 128 * 16, lbo_b = (unsigned)NR * 16;
         const unsigned idesc = idesc_tf32(128, N);
         const unsigned a0 = smem_u32(smem), b0 = smem_u32(smem + 128 * KP);
@@ -171,39 +141,50 @@ __global__ void __launch_bounds__(32 * 9, 1) time_kernel(long long *out, int N, 
         const unsigned ta0 = tmem_base + 448u, ta1 = tmem_base + 456u;
         const unsigned d0 = tmem_base, d1 = tmem_base + (ndst > 1 ? 192u : 0u);
         long long t0 = clock64();
-        if (ts) {
-            for (int i = 0; i < count; i += 4) {
-                mma_tf32_ts_elect(d0, ta0, db0, idesc, 1u);
-                mma_tf32_ts_elect(d1, ta1, db1, idesc, 1u);
-                mma_tf32_ts_elect(d0, ta1, db1, idesc, 1u);
-                mma_tf32_ts_elect(d1, ta0, db0, idesc, 1u);
-            }
-        } else {
-            for (int i = 0; i < count; i += 4) {
-                mma_tf32_elect(d0, da0, db0, idesc, 1u);
-                mma_tf32_elect(d1, da1, db1, idesc, 1u);
-                mma_tf32_elect(d0, da1, db1, idesc, 1u);
-                mma_tf32_elect(d1, da0, db0, idesc, 1u);
+        if (elect_one()) {
+            if (ts) {
+                for (int i = 0; i < count; i += 4) {
+                    mma_tf32_ts(d0, ta0, db0, idesc, 1u);
+                    mma_tf32_ts(d1, ta1, db1, idesc, 1u);
+                    mma_tf32_ts(d0, ta1, db1, idesc, 1u);
+                    mma_tf32_ts(d1, ta0, db0, idesc, 1u);
+                }
+            } else {
+                for (int i = 0; i < count; i += 4) {
+                    mma_tf32(d0, da0, db0, idesc, 1u);
+                    mma_tf32(d1, da1, db1, idesc, 1u);
+                    mma_tf32(d0, da1, db1, idesc, 1u);
+                    mma_tf32(d1, da0, db0, idesc, 1u);
+                }
             }
         }
+        __syncwarp();
         long long t1 = clock64();
         mma_commit_elect(&bar);
         mbar_wait(&bar, 0);
         long long t2 = clock64();
         if ((tid & 31) == 0) { out[0] = t1 - t0; out[1] = t2 - t0; done = 1; }
-    } else if (warp < hammer) {
-        const float4 *base = reinterpret_cast<const float4 *>(smem + (128 + NR) * KP) + (tid & 31);
-        float4 acc = make_float4(0, 0, 0, 0);
+    } else {
+        volatile float4 *base = reinterpret_cast<volatile float4 *>(smem + (128 + NR) * KP) + (tid & 31);
+        const unsigned tcol = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + 384u + (unsigned)((warp >> 2) * 16);
+        float acc = 0.f;
         long long n = 0;
+        float v16[16];
+        for (int j = 0; j < 16; ++j) v16[j] = (float)j;
         while (!done) {
+            if (hammer & 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float4 v = base[32 * ((j + warp) & 63)];
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                for (int j = 0; j < 8; ++j) { acc += base[32 * ((j + warp) & 63)].x; }
             }
-            n += 16;
+            if (hammer & 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { base[32 * ((j + warp) & 63)].y = acc; }
+            }
+            if (hammer & 4) { tmem_st16(tcol, v16); tmem_st_wait(); }
+            if (hammer & 8) { tmem_ld16(tcol, v16); tmem_ld_wait(); acc += v16[3]; }
+            n += 1;
         }
-        if (acc.x == 123.f) sink[tid] = acc.x + acc.y + acc.z + acc.w;
+        if (acc == 123.f) sink[tid] = acc;
         if ((tid & 31) == 0) out[2 + warp] = n;
     }
     tc_fence_before();
@@ -225,10 +206,10 @@ static void time_it(int N, int count, int ndst, int ts, int hammer) {
         if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(1); }
     }
     cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
-    double lds = 0;
-    for (int w = 0; w < hammer; ++w) lds += (double)h[2 + w];
-    printf("%s N=%3d ndst=%d hammer=%d : issue %.1f clk/mma  complete %.1f clk/mma (ideal %.1f)   LDS.128 %.2f warp-instr/clk (4 wavefronts each)\n",
-           ts ? "TS" : "SS", N, ndst, hammer, (double)h[0] / count, (double)h[1] / count, N / 2.0, lds / (double)h[1]);
+    double loops = 0;
+    for (int w = 0; w < 8; ++w) loops += (double)h[2 + w];
+    printf("%s N=%3d ndst=%d hammer=%2d : issue %.1f clk/mma  complete %.1f clk/mma (ideal %.1f)   hammer loops/kclk (8 warps) %.1f\n",
+           ts ? "TS" : "SS", N, ndst, hammer, (double)h[0] / count, (double)h[1] / count, N / 2.0, 1e3 * loops / (double)h[1]);
     cudaFree(d);
     cudaFree(sink);
 }
