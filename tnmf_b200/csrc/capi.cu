@@ -97,6 +97,18 @@ bool tmem_operand_gradw(const Geo &g, int dtype) {
     return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_gradw_ts_supported(g, dtype);
 }
 
+// The reconstruction with the activation row ring in tensor memory: N = roundup(C * A_x, 16), K = atoms padded to 8, and
+// 128 - (A_x - 1) of the 128 MMA lanes produce outputs; 'auto' takes it when at least half of every MMA is useful work.
+bool tmem_operand_recon(const Geo &g, int dtype) {
+    return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_recon_ts_supported(g, dtype);
+}
+bool tc_recon_ts_worthwhile(const Geo &g) {
+    if (g.flags & TNMF_FLAG_NO_TC_RECON) return false;
+    const int nu = g.C * g.A[2], np = (nu + 15) / 16 * 16, km = (g.M + 7) / 8 * 8;
+    const double useful = ((double)nu / np) * ((double)g.M / km) * (double)(128 - (g.A[2] - 1)) / 128.0;
+    return useful >= 0.5 && (long long)g.N * g.D[2] >= 128;
+}
+
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;
 // a forced family that cannot serve the problem is an error.
 int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
@@ -104,6 +116,9 @@ int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
     if (p->path == TNMF_PATH_GENERIC) return TNMF_PATH_GENERIC;
     if (op == TNMF_OP_GRADIENT_H && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_worthwhile(g))) &&
         tc_hupd_supported(g, p->dtype))
+        return TNMF_PATH_TC;
+    if (op == TNMF_OP_RECONSTRUCT && tmem_operand_recon(g, p->dtype) &&
+        (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_ts_worthwhile(g))))
         return TNMF_PATH_TC;
     if (op == TNMF_OP_RECONSTRUCT && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_worthwhile(g))) &&
         tc_recon_supported(g, p->dtype))
@@ -228,6 +243,8 @@ int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *
     cudaStream_t st = (cudaStream_t)stream;
     int family = choose_family(p, g, TNMF_OP_RECONSTRUCT, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TC && tmem_operand_recon(g, p->dtype))
+        return tc_reconstruct_ts(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
     if (family == TNMF_PATH_TC)
         return tc_reconstruct(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
     if (family == TNMF_PATH_TMA && (!aligned16(H) || !workspace)) {
@@ -268,7 +285,9 @@ int tnmf_reconstruct_energy(const tnmf_problem *p, const void *V, const void *W,
         family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
     }
     const bool tiled = family == TNMF_PATH_TILED;
-    if (family == TNMF_PATH_TC) {
+    if (family == TNMF_PATH_TC && tmem_operand_recon(g, p->dtype)) {
+        s = tc_reconstruct_ts(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials, st);
+    } else if (family == TNMF_PATH_TC) {
         s = tc_reconstruct(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials, st);
     } else if (family == TNMF_PATH_TMA) {
         partials = tma_energy_partials(g, workspace);

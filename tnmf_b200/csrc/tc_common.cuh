@@ -123,6 +123,34 @@ __device__ __forceinline__ void mma_tf32_ts(unsigned tmem_d, unsigned tmem_a, un
         "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, the B descriptor given as its two 32-bit words (only the low word - start address | LBO - changes between MMAs, so
+// the issuing loop advances it with one uniform add) and always accumulating / never accumulating.
+template <bool kAccumulate>
+__device__ __forceinline__ void mma_tf32_ts2(unsigned tmem_d, unsigned tmem_a, unsigned desc_b_lo, unsigned desc_b_hi,
+                                             unsigned idesc) {
+    if constexpr (kAccumulate)
+        asm volatile(
+            "{\n"
+            ".reg .b64 d;\n"
+            ".reg .pred p;\n"
+            "mov.b64 d, {%2, %3};\n"
+            "setp.eq.b32 p, 0, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "r"(tmem_a), "r"(desc_b_lo), "r"(desc_b_hi), "r"(idesc)
+            : "memory");
+    else
+        asm volatile(
+            "{\n"
+            ".reg .b64 d;\n"
+            ".reg .pred p;\n"
+            "mov.b64 d, {%2, %3};\n"
+            "setp.ne.b32 p, 0, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n"
+            "}\n" ::"r"(tmem_d),
+            "r"(tmem_a), "r"(desc_b_lo), "r"(desc_b_hi), "r"(idesc)
+            : "memory");
+}
 __device__ __forceinline__ void mma_commit_elect(unsigned long long *bar) {
     asm volatile(
         "{\n"

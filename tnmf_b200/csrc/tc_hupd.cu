@@ -127,7 +127,9 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
     __shared__ __align__(8) unsigned long long a_full[kMaxStages], a_empty[kMaxStages], row_done[kSlots],
         slot_free[kSlots];
     __shared__ unsigned tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index out of a shuffle: ptxas then knows the role branches are warp-uniform and keeps the MMA issuers' operands in
+    // uniform registers (tc_gradw_ts.cu has the measurements)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int KP = p.KP, AY = g.AY, AX = g.AX, C = g.C;
     const int NR = AY * kNB;                               // rows of the atom operand
     float *w_hi = smem, *w_lo = smem + NR * KP;
@@ -355,8 +357,10 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
         const unsigned lbo_a = kTile * 16, lbo_b = (unsigned)NR * 16;
         const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
         const unsigned a_lo_word = ((lbo_a >> 4) << 16), b_lo_word = ((lbo_b >> 4) << 16);
-        const unsigned w_addr16[3] = {smem_u32(w_hi) >> 4, smem_u32(w_hi) >> 4, smem_u32(w_lo) >> 4};
-        const unsigned stage_addr0 = smem_u32(stages);
+        const unsigned w_hi16 = __shfl_sync(0xffffffffu, smem_u32(w_hi) >> 4, 0), w_lo16 = __shfl_sync(0xffffffffu, smem_u32(w_lo) >> 4, 0);
+        const unsigned w_addr16[3] = {w_hi16, w_hi16, w_lo16};
+        const unsigned stage_addr0 = __shfl_sync(0xffffffffu, smem_u32(stages), 0);
+        const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const unsigned a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4;
         const int x = warp - 12;                // warp 12 issues the V stages (neg accumulators), warp 13 the R stages (pos)
         int st = x;
@@ -408,32 +412,35 @@ hupd_tc_kernel(const Geo2 g, const TcHupdPlan p, const TcHupdArgs a) {
                 {
                     TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
                     tc_fence_after();
-                    const unsigned col_base = tmem_base + (x ? 256u : 0u);
+                    const unsigned col_base = tmem_u + (x ? 256u : 0u);
                     const unsigned a_hi16 = (stage_addr0 + (unsigned)st * (unsigned)p.stage_floats * 4u) >> 4;
                     const unsigned a_addr16[3] = {a_hi16, a_hi16 + ((kTile * KP * 4u) >> 4), a_hi16};
-                    for (int ks = 0; ks < p.ksteps; ++ks) {
+                    if (elect_one()) {              // one election per stage: operands go to uniform registers once
+                        for (int ks = 0; ks < p.ksteps; ++ks) {
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const unsigned long long da =
-                                ((unsigned long long)desc_hi << 32) | (a_lo_word | (a_addr16[t] + ks * a_step16));
-                            const unsigned b16 = w_addr16[t] + ks * b_step16;
-                            if (ks == 0 && t == 0 && n_first > 0) {
+                            for (int t = 0; t < 3; ++t) {
+                                const unsigned long long da =
+                                    ((unsigned long long)desc_hi << 32) | (a_lo_word | (a_addr16[t] + ks * a_step16));
+                                const unsigned b16 = w_addr16[t] + ks * b_step16;
+                                if (ks == 0 && t == 0 && n_first > 0) {
 #pragma unroll
-                                for (int o = 0; o < 4; ++o)
-                                    if (o < n_first)
-                                        mma_tf32_elect(col_base + f_col[o], da,
-                                                 ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + f_b16[o])),
-                                                 f_idesc[o], o < n_old ? 1u : 0u);
-                            } else {
-                                mma_tf32_elect(col_base + o_col[0], da,
-                                         ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[0])), o_idesc[0], 1u);
-                                if (n_ops > 1)
-                                    mma_tf32_elect(col_base + o_col[1], da,
-                                             ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[1])),
-                                             o_idesc[1], 1u);
+                                    for (int o = 0; o < 4; ++o)
+                                        if (o < n_first)
+                                            mma_tf32(col_base + f_col[o], da,
+                                                     ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + f_b16[o])),
+                                                     f_idesc[o], o < n_old ? 1u : 0u);
+                                } else {
+                                    mma_tf32(col_base + o_col[0], da,
+                                             ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[0])), o_idesc[0], 1u);
+                                    if (n_ops > 1)
+                                        mma_tf32(col_base + o_col[1], da,
+                                                 ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16[1])),
+                                                 o_idesc[1], 1u);
+                                }
                             }
                         }
                     }
+                    __syncwarp();
                     mma_commit_elect(&a_empty[st]);
                     st += 2;
                     if (st >= p.n_stages) { st = x; ph ^= 1u; }

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) recon_tc_kernel(const Geo2 g, con
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long a_full[kMaxStages], a_empty[kMaxStages], d_full[kBufs], d_free[kBufs];
     __shared__ unsigned tmem_base_s;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // warp index out of a shuffle: warp-uniform role branches, MMA operands in uniform registers (see tc_gradw_ts.cu)
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int KM = p.KM, AY = g.AY, AX = g.AX;
     float *b_hi = smem, *b_lo = smem + p.b_floats;
     float *stages = b_lo + p.b_floats;                          // [stage][hi, lo][stage_floats]
@@ -277,8 +278,10 @@ __global__ void __launch_bounds__(kThreads, 1) recon_tc_kernel(const Geo2 g, con
         const unsigned lbo_a = (unsigned)p.RWSp * 16, lbo_b = (unsigned)NP * 16;
         const unsigned desc_hi = (128u >> 4) | (1u << 14);                      // SBO, descriptor version 1
         const unsigned a_lo_word = ((lbo_a >> 4) << 16), b_lo_word = ((lbo_b >> 4) << 16);
-        const unsigned b16[3] = {smem_u32(b_hi) >> 4, smem_u32(b_hi) >> 4, smem_u32(b_lo) >> 4};
-        const unsigned stage_addr0 = smem_u32(stages);
+        const unsigned b_hi16 = __shfl_sync(0xffffffffu, smem_u32(b_hi) >> 4, 0), b_lo16 = __shfl_sync(0xffffffffu, smem_u32(b_lo) >> 4, 0);
+        const unsigned b16[3] = {b_hi16, b_hi16, b_lo16};
+        const unsigned stage_addr0 = __shfl_sync(0xffffffffu, smem_u32(stages), 0);
+        const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         const unsigned a_step16 = (2 * lbo_a) >> 4, b_step16 = (2 * lbo_b) >> 4, b_ax16 = ((unsigned)(NP * KM) * 4u) >> 4;
         const unsigned idesc = idesc_tf32(kTile, NP);
         long long g_row = 0;
@@ -295,22 +298,25 @@ __global__ void __launch_bounds__(kThreads, 1) recon_tc_kernel(const Geo2 g, con
                 tc_fence_after();
                 const unsigned a_hi16 = (stage_addr0 + (unsigned)st * 2u * (unsigned)p.stage_floats * 4u) >> 4;
                 const unsigned a_addr16[3] = {a_hi16, a_hi16 + (((unsigned)p.stage_floats * 4u) >> 4), a_hi16};
-                const unsigned tbuf = tmem_base + (unsigned)(buf * 64);
-                unsigned acc = 0u;
-                for (int ax = 0; ax < AX; ++ax) {
-                    const unsigned shift16 = (unsigned)(AX - 1 - ax);       // operand rows start AX-1-ax rows into the tile
-                    for (int ks = 0; ks < p.ksteps; ++ks) {
+                const unsigned tbuf = tmem_u + (unsigned)(buf * 64);
+                if (elect_one()) {                  // one election per source row: operands go to uniform registers once
+                    unsigned acc = 0u;
+                    for (int ax = 0; ax < AX; ++ax) {
+                        const unsigned shift16 = (unsigned)(AX - 1 - ax);   // operand rows start AX-1-ax rows into the tile
+                        for (int ks = 0; ks < p.ksteps; ++ks) {
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            const unsigned long long da = ((unsigned long long)desc_hi << 32) |
-                                                          (a_lo_word | (a_addr16[t] + shift16 + ks * a_step16));
-                            const unsigned long long db = ((unsigned long long)desc_hi << 32) |
-                                                          (b_lo_word | (b16[t] + ax * b_ax16 + ks * b_step16));
-                            mma_tf32_elect(tbuf, da, db, idesc, acc);
-                            acc = 1u;
+                            for (int t = 0; t < 3; ++t) {
+                                const unsigned long long da = ((unsigned long long)desc_hi << 32) |
+                                                              (a_lo_word | (a_addr16[t] + shift16 + ks * a_step16));
+                                const unsigned long long db = ((unsigned long long)desc_hi << 32) |
+                                                              (b_lo_word | (b16[t] + ax * b_ax16 + ks * b_step16));
+                                mma_tf32(tbuf, da, db, idesc, acc);
+                                acc = 1u;
+                            }
                         }
                     }
                 }
+                __syncwarp();
                 mma_commit_elect(&a_empty[st]);
                 mma_commit_elect(&d_full[buf]);
             }
