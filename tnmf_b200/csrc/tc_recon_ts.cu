@@ -81,6 +81,9 @@ bool make_plan(const Geo2 &g, Plan &p) {
     if (2 * p.RS * p.KM + 2 * p.NP > 512) return false;
     p.NBUF = (512 - 2 * p.RS * p.KM) / p.NP;
     if (p.NBUF > kBufMax) p.NBUF = kBufMax;
+    // even: a P buffer then always belongs to the same issuing warp and the same epilogue group.  A barrier watched by
+    // alternating waiters would be watched every other phase only, and a parity wait cannot tell phase u from phase u - 2.
+    p.NBUF &= ~1;
     while (p.RS < kRingMax && 2 * (p.RS + 1) * p.KM + p.NBUF * p.NP <= 512) ++p.RS;
     p.p_col0 = 2 * p.RS * p.KM;
     p.VW = g.DX + g.AX - 1;
@@ -259,14 +262,19 @@ __global__ void __launch_bounds__(kThreads, 1) recon_ts_kernel(const Geo2 g, con
 #ifdef TNMF_TC_PROFILE
                 const long long t_l = clock64();
 #endif
-                for (int c0 = 0; c0 < NP; c0 += 32) {                 // two chunks of 16 columns in flight
-                    float v[2][16];
-                    tmem_ld16(lane_base + (unsigned)(my_buf * NP + c0), v[0]);
-                    if (c0 + 16 < NP) tmem_ld16(lane_base + (unsigned)(my_buf * NP + c0 + 16), v[1]);
-                    tmem_ld_wait();
+                if (NP <= 48) {
+                    // all columns of the row in registers first: the P buffer goes back to its issuer after one TMEM round trip
+                    float v[3][16];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int cc = c0 + 16 * h;
+                    for (int h = 0; h < 3; ++h)
+                        if (16 * h < NP) tmem_ld16(lane_base + (unsigned)(my_buf * NP + 16 * h), v[h]);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_free[my_buf]);
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) {
+                        const int cc = 16 * h;
                         float *pd = ps + cc * kTile + i;
                         if (cc + 16 <= NU) {
 #pragma unroll
@@ -277,10 +285,30 @@ __global__ void __launch_bounds__(kThreads, 1) recon_ts_kernel(const Geo2 g, con
                                 if (cc + k < NU) pd[k * kTile] = v[h][k];
                         }
                     }
+                } else {
+                    for (int c0 = 0; c0 < NP; c0 += 32) {             // two chunks of 16 columns in flight
+                        float v[2][16];
+                        tmem_ld16(lane_base + (unsigned)(my_buf * NP + c0), v[0]);
+                        if (c0 + 16 < NP) tmem_ld16(lane_base + (unsigned)(my_buf * NP + c0 + 16), v[1]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int cc = c0 + 16 * h;
+                            float *pd = ps + cc * kTile + i;
+                            if (cc + 16 <= NU) {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k) pd[k * kTile] = v[h][k];
+                            } else if (cc < NU) {
+#pragma unroll
+                                for (int k = 0; k < 16; ++k)
+                                    if (cc + k < NU) pd[k * kTile] = v[h][k];
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&p_free[my_buf]);
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&p_free[my_buf]);
 #ifdef TNMF_TC_PROFILE
                 prof_ld += clock64() - t_l;
 #endif
