@@ -93,6 +93,9 @@ bool tc_gradw_worthwhile(const Geo &g) {
 }
 
 // Tensor-core kernels whose expanded operand lives in tensor memory (tc_*_ts.cu) take over wherever they plan
+bool tmem_operand_hupd(const Geo &g, int dtype) {
+    return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_hupd_ts_supported(g, dtype);
+}
 bool tmem_operand_gradw(const Geo &g, int dtype) {
     return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_gradw_ts_supported(g, dtype);
 }
@@ -115,7 +118,7 @@ int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
     *err = TNMF_OK;
     if (p->path == TNMF_PATH_GENERIC) return TNMF_PATH_GENERIC;
     if (op == TNMF_OP_GRADIENT_H && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_worthwhile(g))) &&
-        tc_hupd_supported(g, p->dtype))
+        (tc_hupd_supported(g, p->dtype) || tmem_operand_hupd(g, p->dtype)))
         return TNMF_PATH_TC;
     if (op == TNMF_OP_RECONSTRUCT && tmem_operand_recon(g, p->dtype) &&
         (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_ts_worthwhile(g))))
@@ -319,6 +322,9 @@ static int gradient_h_dispatch(const tnmf_problem *p, const void *V, const void 
     cudaStream_t st = (cudaStream_t)stream;
     int family = choose_family(p, g, TNMF_OP_GRADIENT_H, &s);
     if (s) return s;
+    if (family == TNMF_PATH_TC && tmem_operand_hupd(g, p->dtype))
+        return tc_gradient_h_ts(g, (const float *)V, (const float *)R, (const float *)W, (float *)neg, (float *)pos,
+                                (float *)H, reg, (const float *)G, lambda, (const float *)Gsum, lambda_cross, st);
     if (family == TNMF_PATH_TC)
         return tc_gradient_h(g, (const float *)V, (const float *)R, (const float *)W, (float *)neg, (float *)pos,
                              (float *)H, reg, (const float *)G, lambda, (const float *)Gsum, lambda_cross, st);

@@ -112,6 +112,11 @@ int tc_recon_partials(const Geo &g);
 int tc_reconstruct(const Geo &g, const float *W, const float *H, float *R, const float *V, double *energy_partials,
                    int *n_partials, cudaStream_t st);
 
+// ---- implemented in tc_hupd_ts.cu (tcgen05 3xTF32, expanded operand in tensor memory) ---------------------------
+bool tc_hupd_ts_supported(const Geo &g, int dtype);
+int tc_gradient_h_ts(const Geo &g, const float *V, const float *R, const float *W, float *neg, float *pos, float *H,
+                     double reg, const float *G, double lambda, const float *Gsum, double lambda_cross, cudaStream_t st);
+
 // ---- implemented in tc_recon_ts.cu (tcgen05 3xTF32, activation row ring in tensor memory) ---------------------
 bool tc_recon_ts_supported(const Geo &g, int dtype);
 int tc_recon_ts_partials(const Geo &g);
