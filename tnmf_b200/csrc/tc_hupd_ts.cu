@@ -19,10 +19,10 @@
 // finished row is drained in two halves: neg after the V stage that completes it (while the R stage runs), pos after the
 // R stage (while the next V stage runs).  The epilogue zeroes a slot when it has read it, so every MMA accumulates.
 //
-// Roles (448 threads): warps 0-3 expand V rows, warps 4-7 R rows (thread = column = TMEM lane); warp 8 issues the V stages
+// Roles (576 threads): warps 0-3 expand V rows, warps 4-7 R rows (thread = column = TMEM lane); warp 8 issues the V stages
 // (neg ring), warp 9 the R stages (pos ring) - converged warps, one election per stage, operands in uniform registers - and
 // they take turns (V(r), R(r), V(r+1), ...: while one tensor's MMAs run, the other tensor's next row is expanded into its
-// single operand buffer); warps 10-13 run the epilogue.  mbarriers: a_full/a_empty per tensor, {neg,pos}_{done,free} per
+// single operand buffer); warps 10-17 run the epilogue (two warps per TMEM lane quarter, eight atoms each).  mbarriers: a_full/a_empty per tensor, {neg,pos}_{done,free} per
 // ring slot, turn per issuer.  Atoms in blocks of 16 (one launch per block).
 #include "tc_common.cuh"
 
@@ -36,7 +36,7 @@ using tiled::round_up;
 
 constexpr int kTile = 128;          // activation columns per CTA tile = MMA M
 constexpr int kNB = 16;             // atoms per launch
-constexpr int kThreads = 32 * 14;
+constexpr int kThreads = 32 * 18;     // 8 expander + 2 MMA-issuing + 8 epilogue warps
 constexpr int kRingMax = 16;
 constexpr int kRawMax = 8;          // raw-row elements per expander thread (C * (128 + AX - 1) <= 1024)
 constexpr int kMaxSmem = 226 * 1024;
@@ -50,6 +50,8 @@ struct Plan {
     long long units;
     int grid;
     size_t smem;
+    int koff[64];                   // k = (c, ax) -> c * RW + ax: offset of the tap in a raw row (kernel parameters live in
+                                    // the constant bank: the expanders add them as immediate-like operands)
 };
 
 struct Args {
@@ -78,6 +80,7 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.raw_floats = round_up(g.C * p.RW, 32);
     p.nraw = ceil_div(g.C * p.RW, 128);
     if (p.nraw > kRawMax) return false;
+    for (int k = 0; k < 64; ++k) p.koff[k] = k < p.KPL ? (k / g.AX) * p.RW + (k % g.AX) : 0;
     p.smem = (size_t)p.w_floats * 4 + (size_t)4 * p.raw_floats * 4 + 1024;
     if (p.smem > (size_t)kMaxSmem) return false;
     const long long cols = (long long)g.N * p.TXP;
@@ -112,6 +115,8 @@ __device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan
     return w;
 }
 
+// KPT = KP: compile-time contraction length (the expansion is fully unrolled: all loads of a row in flight at once)
+template <int KPT>
 __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, const Plan p, const Args a) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) unsigned long long a_full[2], a_empty[2], turn[2], x_done[2][kRingMax], x_free[2][kRingMax];
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); mbar_init(&turn[s], 1); }
         for (int x = 0; x < 2; ++x)
-            for (int s = 0; s < kRingMax; ++s) { mbar_init(&x_done[x][s], 1); mbar_init(&x_free[x][s], 4); }
+            for (int s = 0; s < kRingMax; ++s) { mbar_init(&x_done[x][s], 1); mbar_init(&x_free[x][s], 8); }
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc(&tmem_base_s, 512);
@@ -169,6 +174,10 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
         const long long plane = (long long)g.DY * g.DX;
         const int raw_count = C * RW;
         unsigned stage = 0, buf = 0;
+        TC_PROF_DECL(empty); TC_PROF_DECL(total); TC_PROF_DECL(bar); TC_PROF_DECL(exp);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             // source element of every raw slot (q = t128 + 128 e -> channel q / RW, position q % RW) in row 0, or -1: zero
@@ -198,49 +207,64 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                 for (int e = 0; e < kRawMax; ++e)
                     if (e < p.nraw && t128 + 128 * e < raw_count) rb[t128 + 128 * e] = rv[e];
                 if (r < w.r_hi) load_raw(r + 1);                    // in flight while this row is expanded and multiplied
-                asm volatile("bar.sync %0, 128;\n" ::"r"(1 + X) : "memory");
-                if (stage) mbar_wait_backoff(&a_empty[X], (stage - 1u) & 1u, 20);
-                tc_fence_after();
-                // window of this column: k = (c, ax) -> rb[c * RW + i + ax], 16 columns of the operand per round trip
+                TC_PROF_WAIT(bar, asm volatile("bar.sync %0, 128;\n" ::"r"(1 + X) : "memory"));
+                // window of this column: k = (c, ax) -> rb[c * RW + ax + i].  All loads are issued before the first use: under
+                // the tensor core's operand traffic a shared-memory round trip costs ~150 clk (measured in tc_recon_ts.cu)
                 const float *pw = rb + i;
-                int ax = 0;
-                for (int k0 = 0; k0 < KP; k0 += 16) {
-                    float v[16];
+                float v[KPT];
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = (k0 + j < p.KPL) ? *pw : 0.f;
-                        ++pw;
-                        if (++ax == AX) { ax = 0; pw += RW - AX; }
-                    }
-                    float hi[16], lo[16];
+                for (int k = 0; k < KPT; ++k) v[k] = k < p.KPL ? pw[p.koff[k]] : 0.f;
+                // the window is in registers before the operand buffer is free: only the split and the stores wait for it
+                if (stage) TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[X], (stage - 1u) & 1u, 20));
+                tc_fence_after();
+#ifdef TNMF_TC_PROFILE
+                const long long t_e = clock64();
+#endif
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) split_tf32(v[j], hi[j], lo[j]);
-                    if (k0 + 16 <= KP) {
+                for (int k0 = 0; k0 < KPT; k0 += 16) {
+                    if (k0 + 16 <= KPT) {
+                        float hi[16], lo[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) split_tf32(v[k0 + j], hi[j], lo[j]);
                         tmem_st16(t_lane + (unsigned)k0, hi);
-                        tmem_st16(t_lane + (unsigned)(KP + k0), lo);
+                        tmem_st16(t_lane + (unsigned)(KPT + k0), lo);
                     } else {                                        // KP is a multiple of 8: a tail of 8 columns
                         float h8[8], l8[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) { h8[j] = hi[j]; l8[j] = lo[j]; }
+                        for (int j = 0; j < 8; ++j) split_tf32(v[k0 + j], h8[j], l8[j]);
                         tmem_st8(t_lane + (unsigned)k0, h8);
-                        tmem_st8(t_lane + (unsigned)(KP + k0), l8);
+                        tmem_st8(t_lane + (unsigned)(KPT + k0), l8);
                     }
                 }
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[X]);
+#ifdef TNMF_TC_PROFILE
+                prof_exp += clock64() - t_e;
+#endif
                 buf ^= 1u;
             }
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && (tid == 0 || tid == 128))
+            printf("hupd_ts expanders X=%d: total %lld  wait a_empty %lld  raw barrier %lld  expansion %lld\n", X, prof_total, prof_empty, prof_bar, prof_exp);
+#endif
     } else if (warp >= 10) {
-        // ------------------------------------ epilogue ------------------------------------
-        const int q = warp & 3;
+        // ------------------------------------ epilogue: warps 10-13 atoms 0-7, warps 14-17 atoms 8-15 of the block ------------------------------------
+        const int q = warp & 3, hs = (warp - 10) >> 2;
+        constexpr int kHA = kNB / 2;
         const int i = q * 32 + lane;
-        const unsigned lane_base = tmem_base + ((unsigned)(q * 32) << 16);
+        const unsigned lane_base = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(hs * kHA);
+        const int ma = a.m0 + hs * kHA;                        // first atom of this thread
         const long long tvol = (long long)g.TY * g.TX;
         int slot = 0;
         unsigned wraps = 0;
+        TC_PROF_DECL(dneg); TC_PROF_DECL(dpos); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             const long long J = (long long)w.tile * kTile + i;
@@ -248,41 +272,41 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
             const int tx = (int)(J - (long long)n * p.TXP);
             const bool active = n < g.N && tx < g.TX;
             // the activations of a row do not depend on the accumulators: they are fetched one row ahead
-            float hnext[kNB];
-            float *hrow = (a.H && active) ? a.H + (long long)n * g.hsn + (long long)a.m0 * g.hsm + tx : nullptr;
+            float hnext[kHA];
+            float *hrow = (a.H && active) ? a.H + (long long)n * g.hsn + (long long)ma * g.hsm + tx : nullptr;
             auto load_h = [&](int ty) {
 #pragma unroll
-                for (int ml = 0; ml < kNB; ++ml)
-                    hnext[ml] = (hrow && a.m0 + ml < g.M) ? hrow[(long long)ty * g.hsy + (long long)ml * g.hsm] : 0.f;
+                for (int ml = 0; ml < kHA; ++ml)
+                    hnext[ml] = (hrow && ma + ml < g.M) ? hrow[(long long)ty * g.hsy + (long long)ml * g.hsm] : 0.f;
             };
             const bool fast = a.H && !a.G && a.m0 + kNB <= g.M;
             load_h(w.ty0);
             for (int ty = w.ty0; ty < w.ty1; ++ty) {
-                float neg[kNB], pos[kNB];
+                float neg[kHA], pos[kHA];
                 // neg: final after the V stage of the row's last source row - drained while the R stage runs
-                mbar_wait_backoff(&x_done[0][slot], wraps & 1u, 20);
+                TC_PROF_WAIT(dneg, mbar_wait_backoff(&x_done[0][slot], wraps & 1u, 20));
                 tc_fence_after();
-                tmem_ld16(lane_base + (unsigned)(slot * kNB), neg);
+                tmem_ld8(lane_base + (unsigned)(slot * kNB), neg);
                 tmem_ld_wait();
-                tmem_st16_zero(lane_base + (unsigned)(slot * kNB));
+                tmem_st8_zero(lane_base + (unsigned)(slot * kNB));
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&x_free[0][slot]);
                 // pos: final after the R stage - drained while the next V stage runs
-                mbar_wait_backoff(&x_done[1][slot], wraps & 1u, 20);
+                TC_PROF_WAIT(dpos, mbar_wait_backoff(&x_done[1][slot], wraps & 1u, 20));
                 tc_fence_after();
-                tmem_ld16(lane_base + (unsigned)(p.pos_col0 + slot * kNB), pos);
+                tmem_ld8(lane_base + (unsigned)(p.pos_col0 + slot * kNB), pos);
                 tmem_ld_wait();
-                tmem_st16_zero(lane_base + (unsigned)(p.pos_col0 + slot * kNB));
+                tmem_st8_zero(lane_base + (unsigned)(p.pos_col0 + slot * kNB));
                 tmem_st_wait();
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&x_free[1][slot]);
                 if (++slot == RS) { slot = 0; ++wraps; }
-                float hv[kNB];
+                float hv[kHA];
 #pragma unroll
-                for (int ml = 0; ml < kNB; ++ml) hv[ml] = hnext[ml];
+                for (int ml = 0; ml < kHA; ++ml) hv[ml] = hnext[ml];
                 if (fast) {
                     // plain fused update of a full block of 16 atoms: pointer walks, no per-atom tests.  The product and the
                     // quotient round separately and to nearest, like the reference's `arr *= neg; arr /= pos`.
@@ -291,10 +315,10 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                         if (ty + 1 < w.ty1) {
                             const float *qn = o + g.hsy;
 #pragma unroll
-                            for (int ml = 0; ml < kNB; ++ml) { hnext[ml] = *qn; qn += g.hsm; }
+                            for (int ml = 0; ml < kHA; ++ml) { hnext[ml] = *qn; qn += g.hsm; }
                         }
 #pragma unroll
-                        for (int ml = 0; ml < kNB; ++ml) {
+                        for (int ml = 0; ml < kHA; ++ml) {
                             *o = __fdiv_rn(__fmul_rn(hv[ml], neg[ml]), __fadd_rn(pos[ml], a.reg));
                             o += g.hsm;
                         }
@@ -305,8 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                 if (!active) continue;
                 const long long tin = (long long)ty * g.TX + tx;
 #pragma unroll
-                for (int ml = 0; ml < kNB; ++ml) {
-                    const int m = a.m0 + ml;
+                for (int ml = 0; ml < kHA; ++ml) {
+                    const int m = ma + ml;
                     if (m >= g.M) continue;
                     const long long cidx = ((long long)n * g.M + m) * tvol + tin;
                     if (a.H) {
@@ -331,6 +355,10 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                 }
             }
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && tid == 320) printf("hupd_ts epilogue: total %lld  wait neg_done %lld  wait pos_done %lld\n", prof_total, prof_dneg, prof_dpos);
+#endif
     } else {
         // ------------------------------------ MMA issuers: warp 8 the V stages, warp 9 the R stages ------------------------------------
         const int X = warp - 8;
@@ -346,6 +374,10 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
         unsigned stage = 0;
         int slot_new = 0, slot_a = 0, slot_done = 0;            // slot of the next row to enter / of the window's first row /
         unsigned wraps_new = 0;                                 // of the next row to complete
+        TC_PROF_DECL(xfree); TC_PROF_DECL(afull); TC_PROF_DECL(turnw); TC_PROF_DECL(issue); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             int next_new = w.ty0, next_done = w.ty0, win0 = w.ty0;
@@ -356,16 +388,19 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                 const int j0 = r + g.offy - AY + 1;                 // output row of atom-row block 0
                 // output rows that receive their first contribution from this source row: their slot must have been drained
                 for (; next_new <= t_b; ++next_new) {
-                    if (wraps_new) mbar_wait(&x_free[X][slot_new], (wraps_new - 1u) & 1u);
+                    if (wraps_new) TC_PROF_WAIT(xfree, mbar_wait(&x_free[X][slot_new], (wraps_new - 1u) & 1u));
                     if (++slot_new == RS) { slot_new = 0; ++wraps_new; }
                 }
                 for (; win0 < t_a; ++win0)
                     if (++slot_a == RS) slot_a = 0;
-                mbar_wait(&a_full[X], stage & 1u);
+                TC_PROF_WAIT(afull, mbar_wait(&a_full[X], stage & 1u));
                 // take turns with the other tensor's warp: V(r), R(r), V(r+1), ...
-                if (X) mbar_wait(&turn[1], stage & 1u);
-                else if (stage) mbar_wait(&turn[0], (stage - 1u) & 1u);
+                if (X) TC_PROF_WAIT(turnw, mbar_wait(&turn[1], stage & 1u));
+                else if (stage) TC_PROF_WAIT(turnw, mbar_wait(&turn[0], (stage - 1u) & 1u));
                 tc_fence_after();
+#ifdef TNMF_TC_PROFILE
+                const long long t_i = clock64();
+#endif
                 // the live rows [t_a, t_b] are one run of ring slots, or two when the window wraps around the ring
                 const int cnt = t_b - t_a + 1;
                 const int first = min(cnt, RS - slot_a);
@@ -386,6 +421,9 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                     }
                 }
                 __syncwarp();
+#ifdef TNMF_TC_PROFILE
+                prof_issue += clock64() - t_i;
+#endif
                 mma_commit_elect(&a_empty[X]);
                 // output rows whose last source row this was
                 for (; next_done < w.ty1 && min(g.DY - 1, next_done - g.offy + AY - 1) <= r; ++next_done) {
@@ -394,11 +432,26 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                 }
             }
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && lane == 0)
+            printf("hupd_ts mma X=%d: total %lld  wait x_free %lld  wait a_full %lld  wait turn %lld  issuing %lld\n", X, prof_total, prof_xfree, prof_afull, prof_turnw, prof_issue);
+#endif
         __syncwarp();
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 8) tmem_dealloc(tmem_base, 512);
+}
+
+template <int KPT>
+static int launch(const Geo2 &g, const Plan &p, const Args &a, cudaStream_t st) {
+    auto kern = hupd_ts_kernel<KPT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (e != cudaSuccess) return status_from_cuda(e);
+    kern<<<(unsigned)p.grid, kThreads, p.smem, st>>>(g, p, a);
+    TNMF_CHECK_LAUNCH();
+    return TNMF_OK;
 }
 
 }  // namespace hut
@@ -423,12 +476,21 @@ int tc_gradient_h_ts(const Geo &g, const float *V, const float *R, const float *
     a.V = V; a.R = R; a.W = W; a.neg = neg; a.pos = pos; a.H = H;
     a.reg = (float)reg; a.lambda = (float)lambda; a.lambda_cross = (float)lambda_cross;
     a.G = G; a.Gsum = Gsum;
-    cudaError_t e = cudaFuncSetAttribute(tc::hut::hupd_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::hut::kMaxSmem);
-    if (e != cudaSuccess) return status_from_cuda(e);
     for (int m0 = 0; m0 < g.M; m0 += tc::hut::kNB) {
         a.m0 = m0;
-        tc::hut::hupd_ts_kernel<<<(unsigned)p.grid, tc::hut::kThreads, p.smem, st>>>(q, p, a);
-        TNMF_CHECK_LAUNCH();
+        int s;
+        switch (p.KP) {
+            case 8: s = tc::hut::launch<8>(q, p, a, st); break;
+            case 16: s = tc::hut::launch<16>(q, p, a, st); break;
+            case 24: s = tc::hut::launch<24>(q, p, a, st); break;
+            case 32: s = tc::hut::launch<32>(q, p, a, st); break;
+            case 40: s = tc::hut::launch<40>(q, p, a, st); break;
+            case 48: s = tc::hut::launch<48>(q, p, a, st); break;
+            case 56: s = tc::hut::launch<56>(q, p, a, st); break;
+            case 64: s = tc::hut::launch<64>(q, p, a, st); break;
+            default: s = TNMF_EUNSUPPORTED;
+        }
+        if (s) return s;
     }
     return TNMF_OK;
 }
