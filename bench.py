@@ -30,6 +30,12 @@ import sys
 import threading
 import time
 
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # The CPU arm uses every host core.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would throttle the BLAS
+    # behind numpy.einsum (round 1: 7.8 -> 2.8 sample-it/s under torchrun); the variables are read when numpy loads.
+    for _v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS'):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -121,14 +127,15 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference's numpy backend on a bounded sample
 # -------------------------------------------------------------------------------------------------------------
-def cpu_oracle_run(w, n_sample, steps, warmup, fourier=True):
+def cpu_oracle_run(w, n_sample, steps, warmup, kind='caching_fft'):
     """Times the MU iteration of the CPU oracle (oracle/tnmf_oracle.py) on `n_sample` samples of workload `w`:
-    OracleNMF_FFT (Fourier-domain form, scipy.fft on all host threads) or OracleNMF (coordinate-space form).
-    Returns (sample-iterations/s, seconds per step)."""
+    OracleNMF_CachingFFT / OracleNMF_FFT (Fourier-domain forms, scipy.fft on all host threads) or OracleNMF
+    (coordinate-space form).  Returns (sample-iterations/s, seconds per step)."""
     from oracle import tnmf_oracle as orc
     rng = np.random.default_rng(0)
     V = rng.random((n_sample, w['C'], *w['D']), dtype=np.float32)
-    nmf = (orc.OracleNMF_FFT if fourier else orc.OracleNMF)(n_atoms=w['M'], atom_shape=w['A'])
+    cls = {'caching_fft': orc.OracleNMF_CachingFFT, 'fft': orc.OracleNMF_FFT, 'direct': orc.OracleNMF}[kind]
+    nmf = cls(n_atoms=w['M'], atom_shape=w['A'])
     np.random.seed(0)
     nmf.initialize(V)
     for _ in range(warmup):
@@ -142,27 +149,81 @@ def cpu_oracle_run(w, n_sample, steps, warmup, fourier=True):
     return n_sample * steps / dt, dt / steps
 
 
+def import_reference():
+    """The UNMODIFIED reference package, if it travelled with the repo: `baseline/_ref` (pip install --target of
+    /root/reference, git-ignored) - with the two `opt_einsum` entry points it uses mapped onto numpy.einsum when that
+    package is absent (tests/golden/_shim, the same shim the golden vectors were generated with).  None otherwise."""
+    ref_dir = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_dir, 'tnmf')):
+        return None
+    try:
+        import opt_einsum  # noqa: F401
+    except ImportError:
+        sys.path.insert(0, os.path.join(ROOT, 'tests', 'golden', '_shim'))
+    sys.path.insert(0, ref_dir)
+    try:
+        from tnmf.TransformInvariantNMF import TransformInvariantNMF as RefNMF
+        return RefNMF
+    except Exception as exc:                                            # pylint: disable=broad-except
+        print(f'reference package present but not importable: {exc!r}', file=sys.stderr)
+        return None
+
+
+def reference_run(RefNMF, w, n_sample, steps, warmup, backend):
+    """Times the reference's own `fit` (stock facade, stock backend) on `n_sample` samples: the iteration loop only,
+    clocked by the progress callback (which also switches the per-iteration energy evaluation off,
+    tnmf/TransformInvariantNMF.py:342-346).  Returns (sample-iterations/s, seconds per step)."""
+    rng = np.random.default_rng(0)
+    V = rng.random((n_sample, w['C'], *w['D']), dtype=np.float32)
+    stamps = []
+    np.random.seed(0)
+    nmf = RefNMF(n_atoms=w['M'], atom_shape=w['A'], backend=backend)
+    nmf.fit(V, n_iterations=warmup + steps, progress_callback=lambda *_: stamps.append(time.perf_counter()) or True)
+    dt = stamps[warmup + steps - 1] - stamps[warmup - 1]
+    return n_sample * steps / dt, dt / steps
+
+
 def run_reference(args, w):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n_sample = CPU_SAMPLE[args.workload]
-    value, s_per_step = cpu_oracle_run(w, n_sample, args.steps, args.warmup, fourier=True)
     n_direct = max(1, n_sample // 2)
-    direct_value, _ = cpu_oracle_run(w, n_direct, 1, 1, fourier=False)
+    RefNMF = import_reference()
+    beside = {}
+    if RefNMF is not None:
+        kind = 'reference'
+        value, s_per_step = reference_run(RefNMF, w, n_sample, args.steps, max(args.warmup, 1), 'numpy_caching_fft')
+        what = ('unmodified emdgroup/tnmf (baseline/_ref): TransformInvariantNMF(backend="numpy_caching_fft").fit, '
+                'iteration loop clocked by the progress callback, scipy.fft workers=-1 (all host threads)')
+        try:
+            nv, _ = reference_run(RefNMF, w, n_direct, 1, 1, 'numpy')
+            beside['numpy'] = {'value': nv, 'unit': UNIT, 'sample': f'{n_direct} samples, 1 warm-up + 1 timed iteration',
+                               'what': 'unmodified reference, backend="numpy" (im2col + BLAS)'}
+        except Exception as exc:                                        # pylint: disable=broad-except
+            beside['numpy'] = {'unavailable': repr(exc)}
+        pv, _ = cpu_oracle_run(w, n_sample, args.steps, max(args.warmup, 1), 'caching_fft')
+        beside['oracle_port'] = {'value': pv, 'unit': UNIT, 'what': 'oracle.OracleNMF_CachingFFT on the same sample '
+                                 '(the port that stands in where the reference package is absent)'}
+    else:
+        kind = 'port'
+        value, s_per_step = cpu_oracle_run(w, n_sample, args.steps, args.warmup, 'caching_fft')
+        what = ('oracle.OracleNMF_CachingFFT: restatement of the reference numpy_caching_fft backend (spectra of V, W, H '
+                'cached between uses), scipy.fft workers=-1 (all host threads); the reference package is not on this box')
+        dv, _ = cpu_oracle_run(w, n_direct, 1, 1, 'direct')
+        beside['numpy_direct'] = {'value': dv, 'unit': UNIT, 'cores': 1,
+                                  'sample': f'{n_direct} samples, 1 warm-up + 1 timed iteration',
+                                  'what': 'oracle.OracleNMF: coordinate-space restatement of the reference numpy '
+                                          'backend (single-threaded shift-and-add)'}
     sample = f'{n_sample} of {w["N"]} samples of {args.workload}, every step one full MU iteration'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * s_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.workload}: {w["text"]}', 'algorithm': 'batch MU', 'cpu_sample': sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample,
-                         'what': 'oracle.OracleNMF_FFT: Fourier-domain restatement of the reference numpy_fft / '
-                                 'numpy_caching_fft backends, scipy.fft workers=-1 (all host threads)',
-                         'numpy_direct': {'value': direct_value, 'unit': UNIT, 'cores': 1,
-                                          'sample': f'{n_direct} samples, 1 warm-up + 1 timed iteration',
-                                          'what': 'oracle.OracleNMF: coordinate-space restatement of the reference '
-                                                  'numpy backend (single-threaded shift-and-add)'}},
+        'config': {'workload': f'{args.workload}: {w["text"]}', 'algorithm': 'batch MU', 'cpu_sample': sample,
+                   'threads': {v: os.environ.get(v) for v in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS')}},
+        'cpu_baseline': dict({'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': kind, 'sample': sample,
+                              'what': what}, **beside),
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -190,6 +251,64 @@ def measure_fp32_peak(lib, torch, device):
         if i >= 2:
             best = max(best, flops.value / (a.elapsed_time(b) * 1e-3) / 1e12)
     return best
+
+
+def time_steps(nmf_cls, w, n_local, device, args, steps, warmup, sharded, dist):
+    """Device time (ms, max over ranks when sharded) of `steps` batch MU iterations on `n_local` resident samples per
+    rank: the same `_batch_step` replay the headline number times."""
+    import torch
+    gen = torch.Generator(device=device)
+    gen.manual_seed(4321 + int(os.environ.get('RANK', '0')))
+    V = torch.rand((n_local, w['C'], *w['D']), dtype=torch.float32, device=device, generator=gen)
+    nmf = nmf_cls(n_atoms=w['M'], atom_shape=w['A'], backend='b200', init='device', distributed=sharded,
+                  input_is_local_shard=True, equal_shards=True, kernel_path=args.kernel_path,
+                  cuda_graph=not args.no_cuda_graph)
+    nmf._initialize_matrices(V, keep_W=False)                            # pylint: disable=protected-access
+    step = nmf._batch_step()                                             # pylint: disable=protected-access
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(device)
+    if sharded:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        step()
+    ev1.record()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    if sharded:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    families = nmf._backend.kernel_families()                            # pylint: disable=protected-access
+    finite = bool(torch.isfinite(nmf.energy_device()).item())
+    del nmf, V, step
+    torch.cuda.empty_cache()
+    return float(ms.item()), families, finite
+
+
+def measure_cfg3(nmf_cls, device, args, world, rank, dist):
+    """BASELINE config 3 on the record of every run: 8192 samples of 1x128x128, 32 atoms 15x15, sharded over the ranks
+    (STRONG scaling: 8192 / N samples per GPU, W-gradient all-reduce every iteration), and - on rank 0, the other ranks
+    waiting - the same 8192 samples on one GPU, so that the line carries its own 1 -> N efficiency."""
+    w3 = WORKLOADS['cfg3']
+    total, steps, warmup = 8192, 5, 3
+    if total % world:
+        return {'skipped': f'{total} samples do not split evenly over {world} ranks'}
+    ms_n, families, finite = time_steps(nmf_cls, w3, total // world, device, args, steps, warmup, world > 1, dist)
+    out = {'workload': 'cfg3: 8192 x 1x128x128, 32 atoms 1x15x15, sample-sharded (strong scaling)', 'samples': total,
+           'samples_per_gpu': total // world, 'steps': steps, 'warmup': warmup, 'ms_per_step': ms_n / steps,
+           'value': total * steps / (ms_n * 1e-3), 'unit': UNIT, 'kernel_path': families, 'finite': finite}
+    if world > 1:
+        ms_1 = None
+        if rank == 0:
+            ms_1, _, _ = time_steps(nmf_cls, w3, total, device, args, 3, 2, False, dist)
+        dist.barrier()
+        if rank == 0:
+            out['single_gpu'] = {'ms_per_step': ms_1 / 3, 'value': total * 3 / (ms_1 * 1e-3), 'steps': 3,
+                                 'what': 'all 8192 samples on rank 0 alone, same run'}
+            out['speedup'] = (ms_1 / 3) / (ms_n / steps)
+            out['efficiency'] = out['speedup'] / world
+    return out
 
 
 def run_b200(args, w):
@@ -291,6 +410,12 @@ def run_b200(args, w):
     d2h = (W_host.size * 4 + 8) / e2e_iters
     assert np.isfinite(e_host)
 
+    cfg3 = None
+    if args.workload == 'cfg2' and not args.no_cfg3:
+        del nmf_e, V_host
+        torch.cuda.empty_cache()
+        cfg3 = measure_cfg3(TransformInvariantNMF, device, args, world, rank, dist)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -358,17 +483,23 @@ def run_b200(args, w):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         n_sample = CPU_SAMPLE[args.workload]
-        cpu_value, _ = cpu_oracle_run(w, n_sample, 3, 1, fourier=True)
-        n_direct = max(1, n_sample // 2)
-        direct_value, _ = cpu_oracle_run(w, n_direct, 1, 1, fourier=False)
-        cpu = {'value': cpu_value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-               'sample': f'{n_sample} of {w["N"]} samples of {args.workload}, 1 warm-up + 3 timed MU iterations',
-               'what': 'oracle.OracleNMF_FFT: Fourier-domain restatement of the reference numpy_fft / '
-                       'numpy_caching_fft backends, scipy.fft workers=-1 (all host threads)',
-               'numpy_direct': {'value': direct_value, 'unit': UNIT, 'cores': 1,
-                                'sample': f'{n_direct} samples, 1 warm-up + 1 timed iteration',
-                                'what': 'oracle.OracleNMF: coordinate-space restatement of the reference numpy '
-                                        'backend (single-threaded shift-and-add)'}}
+        RefNMF = import_reference()
+        sample = f'{n_sample} of {w["N"]} samples of {args.workload}, 1 warm-up + 3 timed MU iterations'
+        if RefNMF is not None:
+            cpu_value, _ = reference_run(RefNMF, w, n_sample, 3, 1, 'numpy_caching_fft')
+            cpu = {'value': cpu_value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'reference', 'sample': sample,
+                   'what': 'unmodified emdgroup/tnmf (baseline/_ref), backend="numpy_caching_fft", all host threads'}
+        else:
+            cpu_value, _ = cpu_oracle_run(w, n_sample, 3, 1, 'caching_fft')
+            n_direct = max(1, n_sample // 2)
+            direct_value, _ = cpu_oracle_run(w, n_direct, 1, 1, 'direct')
+            cpu = {'value': cpu_value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample,
+                   'what': 'oracle.OracleNMF_CachingFFT: restatement of the reference numpy_caching_fft backend, '
+                           'scipy.fft workers=-1 (all host threads)',
+                   'numpy_direct': {'value': direct_value, 'unit': UNIT, 'cores': 1,
+                                    'sample': f'{n_direct} samples, 1 warm-up + 1 timed iteration',
+                                    'what': 'oracle.OracleNMF: coordinate-space restatement of the reference numpy '
+                                            'backend (single-threaded shift-and-add)'}}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -381,7 +512,7 @@ def run_b200(args, w):
                    else 'eager launches',
                    'l2': 'working set (V, R, H) exceeds the 126 MB L2; no explicit flush'
                    if (bytes_step / 5 > 126e6) else 'working set fits L2; iterations overwrite H and R in between',
-                   'final_energy': energy},
+                   'final_energy': energy, 'cfg3': cfg3},
         'roofline': roofline, 'cpu_baseline': cpu,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'what': f'fit(V_host_pinned, n_iterations={e2e_iters}) + W and energy read back; upload, device init '
@@ -403,6 +534,7 @@ def main():
     ap.add_argument('--kernel-path', default='auto', choices=['auto', 'generic', 'tiled', 'tma', 'tc'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-cuda-graph', action='store_true')
+    ap.add_argument('--no-cfg3', action='store_true', help='skip the cfg3 strong-scaling leg of the cfg2 run')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     w = WORKLOADS[args.workload]

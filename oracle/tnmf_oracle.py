@@ -499,3 +499,75 @@ class OracleNMF_FFT(OracleNMF):
 
     def gradient_W(self, s=slice(None)):
         return fft_gradient_W(self.V[s], self.W, self.H[s])
+
+
+class OracleNMF_CachingFFT(OracleNMF_FFT):
+    """OracleNMF_FFT with the spectra kept between uses, the way tnmf/backends/NumPy_CachingFFT.py:52-77,189-281 does:
+    the spectrum of V is computed once per fit, that of W once per W update, that of H once per H update, and the
+    spectrum of the reconstruction is taken from the (cropped) reconstruction once per update.  Same arithmetic as
+    OracleNMF_FFT (tests/test_oracle.py pins it to the coordinate-space oracle); fewer transforms - it is the timed CPU
+    baseline of bench.py wherever the reference package itself is not available."""
+
+    def initialize(self, V: np.ndarray, keep_W: bool = False) -> None:
+        super().initialize(V, keep_W)
+        self._shape = _fft_plan(V.shape[2:], self.atom_shape)
+        self._axes = tuple(range(-len(self.atom_shape), 0))
+        self._Vf = self._rfft(V)
+        self._Wf = None
+        self._Hf = None
+
+    def _rfft(self, X):
+        from scipy.fft import rfftn
+        return rfftn(X, s=self._shape, axes=self._axes, workers=-1)
+
+    def _irfft(self, Xf):
+        from scipy.fft import irfftn
+        return irfftn(Xf, s=self._shape, axes=self._axes, workers=-1)
+
+    def _spectra(self):
+        if self._Wf is None:
+            self._Wf = self._rfft(self.W)
+        if self._Hf is None:
+            self._Hf = self._rfft(self.H)
+        return self._Wf, self._Hf
+
+    def _reconstruct(self):
+        Wf, Hf = self._spectra()
+        full = self._irfft(np.einsum('nm...,mc...->nc...', Hf, Wf, optimize=True))
+        crop = (slice(None), slice(None)) + tuple(slice(a - 1, a - 1 + d) for a, d in zip(self.atom_shape, self.V.shape[2:]))
+        return np.ascontiguousarray(full[crop]).astype(self.H.dtype, copy=False)
+
+    def _take(self, c, shift, out_shape):
+        for ax, (s0, n, L) in enumerate(zip(shift, out_shape, self._shape)):
+            c = np.take(c, np.arange(s0, s0 + n) % L, axis=ax + 2)
+        return c
+
+    def energy(self):
+        return 0.5 * np.sum(np.square(self.V - self._reconstruct()))
+
+    def update_H(self, s=slice(None), sparsity=0.0, inhibition=0.0, cross_inhibition=0.0) -> None:
+        assert inhibition == 0 and cross_inhibition == 0 and s == slice(None), 'times the plain batch MU iteration only'
+        Wf, _ = self._spectra()
+        Rf = self._rfft(self._reconstruct())
+        shift = tuple(-(a - 1) for a in self.atom_shape)
+        out = []
+        for Xf in (self._Vf, Rf):
+            c = self._irfft(np.einsum('mc...,nc...->nm...', np.conj(Wf), Xf, optimize=True))
+            out.append(self._take(c, shift, self.H.shape[2:]).astype(self.H.dtype, copy=False))
+        multiplicative_update(self.H, out[0], out[1], sparsity=sparsity)
+        self._Hf = None
+
+    def gradient_W(self, s=slice(None)):
+        assert s == slice(None)
+        _, Hf = self._spectra()
+        Rf = self._rfft(self._reconstruct())
+        out = []
+        for Xf in (self._Vf, Rf):
+            c = self._irfft(np.einsum('nc...,nm...->mc...', np.conj(Xf), Hf, optimize=True))
+            g = self._take(c, (0,) * len(self.atom_shape), self.atom_shape)
+            out.append(np.ascontiguousarray(np.flip(g, axis=tuple(range(2, g.ndim)))).astype(self.W.dtype, copy=False))
+        return out[0], out[1]
+
+    def update_W(self, s=slice(None)) -> None:
+        super().update_W(s)
+        self._Wf = None

@@ -174,11 +174,31 @@ def test_fft_restatement_fit_follows_direct_fit():
     rng = np.random.default_rng(12)
     V = rng.random((3, 2, 16, 12))
     fits = []
-    for cls in (orc.OracleNMF, orc.OracleNMF_FFT):
+    for cls in (orc.OracleNMF, orc.OracleNMF_FFT, orc.OracleNMF_CachingFFT):
         np.random.seed(4)
         nmf = cls(3, (4, 3))
         nmf.fit_batch(V, n_iterations=8, sparsity_H=0.1)
         fits.append(nmf)
-    assert np.isclose(fits[0].energy(), fits[1].energy(), rtol=1e-9)
-    assert np.allclose(fits[0].W, fits[1].W, rtol=1e-8, atol=1e-12)
-    assert np.allclose(fits[0].H, fits[1].H, rtol=1e-7, atol=1e-12)
+    for other in fits[1:]:          # the Fourier-domain forms (plain and with cached spectra) follow the direct one
+        assert np.isclose(fits[0].energy(), other.energy(), rtol=1e-9)
+        assert np.allclose(fits[0].W, other.W, rtol=1e-8, atol=1e-12)
+        assert np.allclose(fits[0].H, other.H, rtol=1e-7, atol=1e-12)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm): one JSON line, the reference's own
+    package when baseline/_ref is present (kind "reference"), else the caching-FFT port (kind "port")."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OMP_NUM_THREADS='1')             # what torchrun exports: bench.py must undo it
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--workload', 'cfg1',
+                          '--steps', '2', '--warmup', '1'], check=True, capture_output=True, text=True, env=env).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['value'] > 0 and line['gpu_launches'] == 0
+    assert line['cpu_baseline']['kind'] in ('reference', 'port')
+    assert line['cpu_baseline']['kind'] == ('reference' if os.path.isdir(os.path.join(root, 'baseline', '_ref', 'tnmf')) else 'port')
+    assert line['e2e'] == {'value': line['value'], 'unit': line['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert line['config']['threads']['OMP_NUM_THREADS'] == str(os.cpu_count())
