@@ -391,9 +391,9 @@ def run_b200(args, w):
     V_host = V.cpu().pin_memory()
     e2e_iters = args.steps
     nmf_e = TransformInvariantNMF(n_atoms=w['M'], atom_shape=w['A'], backend='b200', init='device',
-                                  input_is_local_shard=True, kernel_path=args.kernel_path,
+                                  input_is_local_shard=True, equal_shards=True, kernel_path=args.kernel_path,
                                   cuda_graph=not args.no_cuda_graph)
-    nmf_e.fit(V_host, n_iterations=1)                                    # warm-up (allocations)
+    nmf_e.fit(V_host, n_iterations=3)                                    # warm-up (allocations, graph capture)
     torch.cuda.synchronize(device)
     if world > 1:
         dist.barrier()
@@ -417,8 +417,7 @@ def run_b200(args, w):
         cfg3 = measure_cfg3(TransformInvariantNMF, device, args, world, rank, dist)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_ranks(world, dist)
         return
 
     # ---- roofline of the dominant kernel -------------------------------------------------------------------------
@@ -520,8 +519,20 @@ def run_b200(args, w):
         'gpu_launches': launches, 'clocks': clocks,
     }
     print(json.dumps(line), flush=True)
+    finish_ranks(world, dist)
+
+
+def finish_ranks(world, dist):
+    """End of a multi-rank run.  The step graphs hold captured NCCL kernels; tearing the communicator down under them
+    was seen to hang at interpreter exit (the JSON line already printed), so the ranks meet once more and leave without
+    running the destructors."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
