@@ -33,6 +33,40 @@ def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class B200Tensor(torch.Tensor):
+    """The tensor type `B200_Backend` hands to the facade: a torch CUDA tensor that also accepts numpy operands.
+
+    The stock facade applies a small set of duck-typed operations to what a backend returns and, in the
+    lateral-inhibition branch, mixes a backend tensor with an ndarray (`inhibition_gradient - self.H[s]`,
+    tnmf/TransformInvariantNMF.py:258).  The reference's own model for a backend-owned array type is
+    tnmf/backends/NumPy_CachingFFT.py:52-77; here every ndarray operand of a torch operation is moved to the tensor's
+    device and dtype first, and numpy defers to the reflected operators (`ndarray - tensor`)."""
+    __array_priority__ = 1000
+    __array_ufunc__ = None          # numpy binary operators return NotImplemented: Python then calls the reflected one here
+
+    def _operand(self, other):
+        return torch.as_tensor(other, dtype=self.dtype).to(self.device) if isinstance(other, np.ndarray) else other
+
+
+def _install_operators():
+    for name in ('add', 'sub', 'mul', 'truediv'):
+        for fmt in ('__{}__', '__r{}__', '__i{}__'):
+            dunder = fmt.format(name)
+            base = getattr(torch.Tensor, dunder)
+
+            def op(self, other, _base=base):
+                return _base(self, self._operand(other))
+            op.__name__ = dunder
+            setattr(B200Tensor, dunder, op)
+
+
+_install_operators()
+
+
+def _facade_tensor(t: torch.Tensor) -> torch.Tensor:
+    return t if isinstance(t, B200Tensor) else t.as_subclass(B200Tensor)
+
+
 class B200_Backend(Backend):  # pylint: disable=invalid-name
     r"""
     Parameters
@@ -331,7 +365,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             W = self._to_device(W, self._dtype)          # a W kept from a run of another backend
         if tuple(W.shape) != w_shape:
             raise ValueError(f'W has shape {tuple(W.shape)}, expected {w_shape}')
-        return W, H
+        return _facade_tensor(W), _facade_tensor(H)
 
     @staticmethod
     def to_ndarray(arr) -> np.ndarray:
@@ -382,7 +416,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             out = dst
         if out is arr:
             out = arr.clone()
-        return out
+        return _facade_tensor(out)
 
     # -----------------------------------------------------------------------------------------------
     # reference interface: the four hot-path operations
@@ -400,7 +434,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             _lib.check(self._lib.tnmf_reconstruct(ctypes.byref(p), W.data_ptr(), H.data_ptr(), R.data_ptr(),
                                                   ws.data_ptr(), ws_bytes, _stream_ptr(self.device)), 'reconstruct')
         self.launches += self._n_launches(p, _lib.OP_RECONSTRUCT)
-        return R
+        return _facade_tensor(R)
 
     def _n_launches(self, p: _lib.Problem, op: int) -> int:
         """Kernels one call of operation `op` launches (the TMA family pre-arranges the atoms in a tiny extra kernel, the
@@ -420,13 +454,13 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
                                              neg.data_ptr(), pos.data_ptr(), ws.data_ptr(), ws_bytes,
                                              _stream_ptr(self.device)), 'gradient_h')
         self.launches += self._n_launches(p, _lib.OP_GRADIENT_H)
-        return neg, pos
+        return _facade_tensor(neg), _facade_tensor(pos)
 
     def reconstruction_gradient_W(self, V, W, H, s: slice = sliceNone):
         """(neg, pos) with the shape of W   (tnmf/backends/_Backend.py:100-108)."""
         out = torch.empty((2, *W.shape), dtype=self._dtype, device=self.device)
         self.gradient_W(V, W, H, s, out)
-        return out[0], out[1]
+        return _facade_tensor(out[0]), _facade_tensor(out[1])
 
     def reconstruction_energy(self, V, W, H) -> float:
         """0.5 * ||V - R||^2 as a Python float   (tnmf/backends/_Backend.py:127-130)."""
