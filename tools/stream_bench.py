@@ -4,14 +4,14 @@ subsamples by `fit_stream` (tnmf/TransformInvariantNMF.py:506-523), each subsamp
 stream while the previous one is being fitted with Cyclic MU over minibatches (:457-465), W is kept from subsample
 to subsample.  Prints one JSON line; the timed region contains every host-to-device copy.
 
-    python tools/stream_bench.py [--signals 16384] [--length 4096] [--atoms 64] [--width 128]
+    python tools/stream_bench.py [--n-signals 16384] [--length 4096] [--atoms 64] [--width 128]
                                  [--subsample 4096] [--batch 1024] [--epochs 3]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/stream_bench.py ...
-        one process per GPU: every rank streams its own `--signals` signals, the W gradient is all-reduced once per
+        one process per GPU: every rank streams its own `--n-signals` signals, the W gradient is all-reduced once per
         epoch, the rate is the job's (all ranks' signals over the slowest rank's time)
 
-`--signals` defaults to 16384 (268 MB of pinned host memory), not BASELINE's 1 M (16 GB): the rate is per signal and
-the stream is consumed subsample by subsample, so the total length only changes the run time.
+`--n-signals` defaults to 16384 (268 MB of pinned host memory); BASELINE config 4 as written is `--n-signals 131072` on
+8 GPUs (1 M signals, 2.1 GB of pinned host memory per rank): profiles/r02_stream_cfg4_n8_1M.json.
 """
 import argparse
 import json
@@ -28,7 +28,7 @@ from tnmf_b200 import MiniBatchAlgorithm, TransformInvariantNMF      # noqa: E40
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--signals', type=int, default=16384)
+    ap.add_argument('--n-signals', dest='signals', type=int, default=16384)
     ap.add_argument('--length', type=int, default=4096)
     ap.add_argument('--atoms', type=int, default=64)
     ap.add_argument('--width', type=int, default=128)
@@ -41,7 +41,7 @@ def main():
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
-    if world > 1:           # torchrun: one process per GPU, every rank streams its own `--signals` signals
+    if world > 1:           # torchrun: one process per GPU, every rank streams its own `--n-signals` signals
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
         torch.distributed.init_process_group('nccl')
     g = torch.Generator().manual_seed(rank)
@@ -52,7 +52,7 @@ def main():
     def run(source):
         np.random.seed(0)
         nmf = TransformInvariantNMF(n_atoms=a.atoms, atom_shape=(a.width,), backend='b200', init=a.init,
-                                    input_is_local_shard=world > 1)
+                                    input_is_local_shard=world > 1, equal_shards=world > 1)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         nmf.fit(source, **kw)
@@ -81,9 +81,12 @@ def main():
         'W_finite': bool(np.isfinite(w).all()), 'W_rows_sum_to_one': bool(np.allclose(w.sum(axis=-1), 1, atol=1e-4)),
     }
     if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+        print(json.dumps(line), flush=True)
+    if world > 1:           # leave without tearing NCCL down under the captured step graphs (see bench.py finish_ranks)
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
