@@ -20,12 +20,14 @@
 // global memory and zeroed), then the operand stages: KS columns of hi + KS of lo each (KS = 32 or 16 tile columns).
 // V taps sit in lanes [0, C*AX), R taps in lanes [64, 64 + C*AX), so all four lane quarters have writers.
 //
-// Roles (416 threads): warps 0-7 workers (warp w writes lane quarter w % 4, column half w / 4 of a stage; together they stage
-// the raw rows and the new activation row), warp 8 issues the MMAs (a converged warp, one elected lane; the live-row window
-// is always one run of ring slots: the first AY - 1 slots are stored a second time behind the last one), warps 9-12 drain the sets.  One issuing warp keeps the
-// order of accumulation into every TMEM column fixed: with two warps taking one run each, a column changed hands between
-// source rows and the warps' relative progress decided which row was added first - run-to-run differences of one ulp
-// (found by tools/determinism_check.py; the tensor core truncates, so the order matters).  mbarriers: a_full/a_empty per operand stage,
+// Roles (448 threads): warps 0-7 workers (warp w writes lane quarter w % 4, column half w / 4 of a stage; together they stage
+// the raw rows and the new activation row), warps 8 and 9 issue the MMAs, each for a FIXED half of the atom rows
+// (converged warps, one elected lane; the live-row window is always one run of ring slots: the first AY - 1 slots are stored
+// a second time behind the last one), warps 10-13 drain the sets.  A TMEM column is written by one warp only, so the order
+// of accumulation is fixed: two warps whose split followed the ring's wrap-around made a column change hands between source
+// rows and their relative progress decide which row was added first - run-to-run differences of one ulp (found by
+// tools/determinism_check.py; the tensor core truncates, so the order matters).  The same happens when two warps take
+// strict turns on the same columns: MMAs of different warps are not executed in the order they were issued.  mbarriers: a_full/a_empty per operand stage,
 // h_full/h_free per ring slot, set_done/set_free per accumulator set.  Atoms in blocks of 16 (one launch per block).
 #include "tc_common.cuh"
 
@@ -40,7 +42,7 @@ using tiled::round_up;
 constexpr int kCT = 64;             // activation columns per tile
 constexpr int kNB = 16;             // atoms per launch
 constexpr int kWorkers = 256;
-constexpr int kIssuers = 1;         // ONE issuing warp: every accumulator column sees its MMAs in program order
+constexpr int kIssuers = 2;         // two issuing warps, each owning a FIXED half of the atom rows (= accumulator columns)
 constexpr int kThreads = 32 * (8 + kIssuers + 4);
 constexpr int kEpoch = 8;           // source rows accumulated into one TMEM set before it is drained
 constexpr int kMaxAStages = 4;
@@ -79,6 +81,7 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.n_sub = kCT / p.KS;
     p.n_astages = spare / (2 * p.KS);
     if (p.n_astages > kMaxAStages) p.n_astages = kMaxAStages;
+    p.n_astages &= ~1;                                      // even: an operand stage always belongs to the same issuing warp
     p.a_col0 = 2 * p.NA;
     p.TXP = g.TX + g.AX - 1;
     p.RW = kCT + g.AX - 1;
@@ -314,28 +317,41 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
 #endif
         auto drain = [&](int e) {
             const int set = (int)(e & 1);
-            TC_PROF_WAIT(done, mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100));
-            tc_fence_after();
             const int l = (warp & 3) * 32 + lane;
             const int X = l >> 6, k = l & 63;
             const bool live = k < p.KPL;
             const int c = live ? k / AX : 0, ax = live ? k - c * AX : 0;
             float *slice = a.partials + (long long)blockIdx.x * 2 * count + (long long)X * count;
             const unsigned tbase = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(set * p.NA);
+            float old_next[kNB];
+#pragma unroll
+            for (int ml = 0; ml < kNB; ++ml) old_next[ml] = 0.f;
+            if (live && !first_drain) {
+                const float *nx = slice + (((long long)a.m0 * C + c) * AY + (AY - 1)) * AX + ax;
+#pragma unroll
+                for (int ml = 0; ml < kNB; ++ml) old_next[ml] = a.m0 + ml < g.M ? __ldcg(nx + ml * (long long)C * AY * AX) : 0.f;
+            }
+            TC_PROF_WAIT(done, mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100));
+            tc_fence_after();
+            // The running sums of the slice do not depend on the set: those of window position 0 were fetched before the
+            // wait above, those of position j + 1 are fetched while position j is added (a drain used to cost 11 dependent
+            // round trips to L2, 22 k clk per epoch against 17 k clk of MMAs: the drainers set the pace).
+            const long long mstride = (long long)C * AY * AX;
+            float *dst_base = slice + (((long long)a.m0 * C + c) * AY) * AX + ax;
             for (int j = 0; j < AY; ++j) {
-                float v[16];
+                float v[16], old[kNB];
+#pragma unroll
+                for (int ml = 0; ml < kNB; ++ml) old[ml] = old_next[ml];
+                if (j + 1 < AY && live && !first_drain) {
+                    const float *nx = dst_base + (long long)(AY - 2 - j) * AX;
+#pragma unroll
+                    for (int ml = 0; ml < kNB; ++ml) old_next[ml] = a.m0 + ml < g.M ? __ldcg(nx + ml * mstride) : 0.f;
+                }
                 tmem_ld16(tbase + (unsigned)(j * kNB), v);
                 tmem_ld_wait();
                 tmem_st16_zero(tbase + (unsigned)(j * kNB));
-                const int ay = AY - 1 - j;
                 if (live) {
-                    // all 16 running sums are fetched before the first store (stores would otherwise order the loads)
-                    float *dst0 = slice + (((long long)a.m0 * C + c) * AY + ay) * AX + ax;
-                    const long long mstride = (long long)C * AY * AX;
-                    float old[kNB];
-#pragma unroll
-                    for (int ml = 0; ml < kNB; ++ml)
-                        old[ml] = (!first_drain && a.m0 + ml < g.M) ? __ldcg(dst0 + ml * mstride) : 0.f;
+                    float *dst0 = dst_base + (long long)(AY - 1 - j) * AX;
 #pragma unroll
                     for (int ml = 0; ml < kNB; ++ml)
                         if (a.m0 + ml < g.M) __stcg(dst0 + ml * mstride, v[ml] + old[ml]);
@@ -369,6 +385,14 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
         const unsigned ring_hi16 = __shfl_sync(0xffffffffu, smem_u32(ring_hi) >> 4, 0);
         const unsigned ring_lo16 = __shfl_sync(0xffffffffu, smem_u32(ring_lo) >> 4, 0);
         const unsigned b_step16 = (2 * lbo_b) >> 4;
+        // Warp X owns the window positions (= atom rows = accumulator column blocks) [j_lo, j_hi]: a TMEM column is only ever
+        // written by one warp, in program order - bitwise reproducible however the two warps interleave - and what one warp
+        // spends between two rows (barrier waits, commits, bookkeeping: ~1000 clk, during which the two-or-three-deep MMA
+        // queue of a single issuer ran dry) is hidden behind the other warp's MMAs.  The split is static because the
+        // mirrored ring never splits a window; a split that moved with the ring's wrap-around made columns change hands
+        // between rows and the accumulation order timing dependent (one-ulp run-to-run differences).
+        const int X = warp - 8;
+        const int j_lo = X ? (AY + 1) / 2 : 0, j_hi = X ? AY - 1 : (AY + 1) / 2 - 1;
         int st = 0;
         unsigned ph = 0;
         int rows_done = 0;
@@ -400,20 +424,21 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
                 }
                 for (; win0 < t_a; ++win0)
                     if (++slot_a == RS) slot_a = 0;
-                // the window [t_a, t_b] is ONE run of physical ring slots (the head of the ring is mirrored behind its tail)
-                const int cnt = t_b - t_a + 1;
-                const int s0 = slot_a;
-                const unsigned col0 = tset + (unsigned)((t_a - j0) * kNB);
-                const unsigned idesc0 = idesc_tf32(128, kNB * cnt);
-                const unsigned b0 = (unsigned)s0 * 16u;
+                // the window [t_a, t_b] is ONE run of physical ring slots (the head of the ring is mirrored behind its tail);
+                // this warp's part of it: [ta_x, tb_x]
+                const int ta_x = max(t_a, j0 + j_lo), tb_x = min(t_b, j0 + j_hi);
+                const int cnt = tb_x - ta_x + 1;
+                const unsigned col0 = tset + (unsigned)((ta_x - j0) * kNB);
+                const unsigned idesc0 = idesc_tf32(128, kNB * max(cnt, 1));
+                const unsigned b0 = (unsigned)(slot_a + (ta_x - t_a)) * 16u;
                 for (int h = 0; h < kCT / KS; ++h) {
                     TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
                     tc_fence_after();
-                    const unsigned ta_hi = tmem_u + (unsigned)(p.a_col0 + st * 2 * KS), ta_lo = ta_hi + KS;
 #ifdef TNMF_TC_PROFILE
                     const long long t_i = clock64();
 #endif
-                    if (elect_one()) {
+                    const unsigned ta_hi = tmem_u + (unsigned)(p.a_col0 + st * 2 * KS), ta_lo = ta_hi + KS;
+                    if (cnt > 0 && elect_one()) {
 #pragma unroll
                         for (int ks = 0; ks < KS / 8; ++ks) {
                             const unsigned kb = (unsigned)(h * (KS / 8) + ks) * b_step16 + b0;
@@ -431,7 +456,8 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
                     mma_commit_elect(&a_empty[st]);
                     if (++st == p.n_astages) { st = 0; ph ^= 1u; }
                 }
-                // activation rows that leave the window: their slots may be overwritten once these MMAs are done
+                // activation rows that leave the window: their slots may be overwritten once these MMAs are done (both
+                // warps commit: h_free counts two arrivals, each commit covers the committing warp's own MMAs)
                 for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r; ++next_out) {
                     mma_commit_elect(&h_free[slot_out]);
                     if (++slot_out == RS) slot_out = 0;
@@ -443,8 +469,8 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
 #ifdef TNMF_TC_PROFILE
         prof_total += clock64();
         if (blockIdx.x == 0 && lane == 0)
-            printf("gradw_ts mma: total %lld  wait a_full %lld  wait h_full %lld  wait set_free %lld  issuing %lld (%d rows)\n",
-                   prof_total, prof_full, prof_hfull, prof_setfree, prof_issue, rows_done);
+            printf("gradw_ts mma %d: total %lld  wait a_full %lld  wait h_full %lld  wait set_free %lld  issuing %lld (%d rows)\n",
+                   X, prof_total, prof_full, prof_hfull, prof_setfree, prof_issue, rows_done);
 #endif
         __syncwarp();
     }
