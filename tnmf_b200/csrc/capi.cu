@@ -109,7 +109,8 @@ bool tc_recon_ts_worthwhile(const Geo &g) {
     if (g.flags & TNMF_FLAG_NO_TC_RECON) return false;
     const int nu = g.C * g.A[2], np = (nu + 15) / 16 * 16, km = (g.M + 7) / 8 * 8;
     const double useful = ((double)nu / np) * ((double)g.M / km) * (double)(128 - (g.A[2] - 1)) / 128.0;
-    return useful >= 0.5 && (long long)g.N * g.D[2] >= 128;
+    // (one-row atoms - 1-D batches run as an image of signal rows - would contract over the atoms only: MMAs too small)
+    return useful >= 0.5 && (long long)g.N * g.D[2] >= 128 && g.A[1] >= 3;
 }
 
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;

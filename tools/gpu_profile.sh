@@ -1,9 +1,9 @@
 # launch list + one full capture of each hot kernel of a bench step (run under gpurun, one GPU); TAG names the outputs,
 # WORKLOAD (default cfg2) the bench workload, KREGEX the kernels of the full capture
 mkdir -p gpurun_out
-T=${TAG:-r03}
+T=${TAG:-r02}
 CMD="python bench.py --workload ${WORKLOAD:-cfg2} --steps 2 --warmup 3 --no-cpu-baseline"
-K=${KREGEX:-hupd_tc_kernel|recon_tc_kernel|gradw_tc_kernel}
+K=${KREGEX:-hupd_ts_kernel|recon_ts_kernel|gradw_ts_kernel}
 $CMD > gpurun_out/${T}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv $CMD > gpurun_out/${T}_ncu_launch.log 2>&1
 $CMD > gpurun_out/${T}_plain2.log 2>&1 &&
