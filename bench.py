@@ -546,9 +546,14 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-cuda-graph', action='store_true')
     ap.add_argument('--no-cfg3', action='store_true', help='skip the cfg3 strong-scaling leg of the cfg2 run')
+    ap.add_argument('--samples', type=int, default=0, help='samples per GPU instead of the workload default '
+                    '(e.g. --workload cfg5 --samples 512: BASELINE config 5 at its full batch)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
-    w = WORKLOADS[args.workload]
+    w = dict(WORKLOADS[args.workload])
+    if args.samples > 0:
+        w['N'] = args.samples
+        w['text'] = f"{w['text']} [--samples {args.samples}]"
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'b200' and args.gpus != world and world == 1 and args.gpus > 1:
         # convenience: relaunch under torchrun when asked for several GPUs from a plain `python bench.py`
