@@ -662,6 +662,44 @@ def test_cuda_graph_replay_equals_eager_launches(kw):
     assert out[False][2] == out[True][2]
 
 
+@pytest.mark.parametrize('graph', (False, True))
+def test_energy_callback_reuses_the_reconstruction(graph):
+    """A callback that reads the energy in every iteration (what the reference's INFO log line does,
+    tnmf/TransformInvariantNMF.py:346) leaves the reconstruction in the backend's R buffer and the next H update opens
+    with it: two reconstruction launches per iteration instead of three, results bit-identical to a fit without callback,
+    energies equal to a fresh evaluation."""
+    from tnmf_b200 import TransformInvariantNMF
+    rng = np.random.default_rng(78)
+    V = rng.random((5, 3, 40, 56)).astype(np.float32)
+    energies, launches, foreign = [], {}, [0]
+
+    def callback(nmf, iteration):
+        energies.append(nmf._energy_function())
+        if iteration == 4:                  # something else writes the R buffer: the next H update must not trust it
+            before = nmf._backend.launches
+            nmf._backend.reconstruction_gradient_H(nmf._V, nmf._W, nmf._H)
+            foreign[0] = nmf._backend.launches - before
+        return True
+
+    out = {}
+    for cb in (None, callback):
+        nmf = TransformInvariantNMF(n_atoms=16, atom_shape=(7, 7), backend='b200', cuda_graph=graph)
+        np.random.seed(9)
+        before = nmf._backend.launches
+        nmf.fit(V, n_iterations=8, progress_callback=cb)
+        launches[cb is not None] = nmf._backend.launches - before
+        out[cb is not None] = (nmf.W.copy(), nmf.H.copy(), nmf._energy_function())
+    assert np.array_equal(out[False][0], out[True][0])
+    assert np.array_equal(out[False][1], out[True][1])
+    assert out[False][2] == out[True][2] == energies[-1]
+    assert all(a > b for a, b in zip(energies, energies[1:]))
+    from tnmf_b200 import _lib
+    per_recon = nmf._backend._n_launches(nmf._backend._last_h_problem, _lib.OP_RECONSTRUCT)
+    # 8 energy evaluations (reconstruction + finishing reduction each) and the foreign call of iteration 4, minus the 6
+    # opening reconstructions that were skipped (iterations 1-7 except the one after the foreign write)
+    assert launches[True] == launches[False] + 8 * (per_recon + 1) + foreign[0] - 6 * per_recon
+
+
 def test_empty_and_single_sample_batches():
     """Ragged minibatches: an empty slice contributes a zero W gradient, a short last batch is served."""
     rng = np.random.default_rng(7)

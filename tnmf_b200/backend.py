@@ -130,6 +130,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self._ws = None
         self.buffers_epoch = 0  # bumped whenever one of the buffers above is replaced (captured CUDA graphs watch it)
         self._energy_buf = None
+        self._R_token = None    # (W pointer, H pointer, samples) whose reconstruction `energy(keep_R=True)` left in _R_buf
         self._problems = {}
         self._taps = {}
         self._last_h_problem = None
@@ -270,7 +271,17 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         if self._R_buf is None or self._R_buf.numel() < numel or self._R_buf.dtype != self._dtype:
             self._R_buf = torch.empty(max(numel, 1), dtype=self._dtype, device=self.device)
             self.buffers_epoch += 1
+        self._R_token = None            # whoever asks for the buffer is about to write it
         return self._R_buf[:numel].view(shape)
+
+    def holds_R_of(self, W: torch.Tensor, H: torch.Tensor) -> bool:
+        """True while the R buffer holds the reconstruction an `energy(..., keep_R=True)` call computed from exactly these
+        tensors and no other operation has written the buffer since (the caller vouches that W and H did not change)."""
+        return self._R_token is not None and self._R_token == (W.data_ptr(), H.data_ptr(), int(H.shape[0]))
+
+    def min_of_V(self) -> torch.Tensor:
+        """Smallest element of the device copy of the samples (a device scalar; the facade's non-negativity assert)."""
+        return torch.amin(self._V_dev) if self._V_dev.numel() else torch.zeros((), device=self.device)
 
     def buffer_tensors(self) -> tuple:
         """The scratch buffers kernels of this backend write to (kept alive by whoever captured their addresses)."""
@@ -469,17 +480,22 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
     # -----------------------------------------------------------------------------------------------
     # fused entry points used by tnmf_b200.TransformInvariantNMF
     # -----------------------------------------------------------------------------------------------
-    def energy(self, V, W, H, s: slice = sliceNone) -> torch.Tensor:
-        """Device-resident double scalar 0.5*||V[s] - reconstruct(W, H[s])||^2 (no host synchronisation)."""
+    def energy(self, V, W, H, s: slice = sliceNone, keep_R: bool = False) -> torch.Tensor:
+        """Device-resident double scalar 0.5*||V[s] - reconstruct(W, H[s])||^2 (no host synchronisation).  With `keep_R`
+        the reconstruction is also written to the R buffer, where `update_H(..., reuse_R=True)` picks it up."""
         Hs = H[s]
         Vs = self._device_V(V)[s]
+        keep_R = keep_R and Hs.shape[0] > 0 and Hs.data_ptr() == H.data_ptr() and Hs.shape[0] == H.shape[0]
+        R = self._R_for(Hs.shape[0]) if keep_R else None
         p, Hs = self._h_problem(Hs)
         ws, ws_bytes = self._workspace(p)
         e = torch.empty((), dtype=torch.float64, device=self.device)
-        _lib.check(self._lib.tnmf_reconstruct_energy(ctypes.byref(p), Vs.data_ptr(), W.data_ptr(), Hs.data_ptr(), None,
-                                                     e.data_ptr(), ws.data_ptr(), ws_bytes, _stream_ptr(self.device)),
-                   'reconstruct_energy')
+        _lib.check(self._lib.tnmf_reconstruct_energy(ctypes.byref(p), Vs.data_ptr(), W.data_ptr(), Hs.data_ptr(),
+                                                     R.data_ptr() if keep_R else None, e.data_ptr(), ws.data_ptr(),
+                                                     ws_bytes, _stream_ptr(self.device)), 'reconstruct_energy')
         self.launches += 1 + self._n_launches(p, _lib.OP_RECONSTRUCT)
+        if keep_R:
+            self._R_token = (W.data_ptr(), Hs.data_ptr(), int(Hs.shape[0]))
         return e
 
     def _inhibition_taps(self, kernels: Sequence[np.ndarray]):
@@ -492,7 +508,7 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
 
     def update_H(self, V, W, H, s: slice = sliceNone, sparsity: float = 0., inhibition: float = 0.,
                  cross_inhibition: float = 0., inhibition_kernels: Optional[Sequence[np.ndarray]] = None,
-                 eps: float = 1.e-9) -> None:
+                 eps: float = 1.e-9, reuse_R: bool = False) -> None:
         """One in-place multiplicative update of H[s]: reconstruct, both correlations, sparsity / inhibition terms and
         H <- (H*neg)/pos in one fused kernel   (tnmf/TransformInvariantNMF.py:246-271 + :217-235)."""
         Hs = H[s]
@@ -500,7 +516,10 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
             return
         Vs = self._device_V(V)[s]
         n = Hs.shape[0]
-        R = self.reconstruct(W, Hs, out=self._R_for(n))
+        have_R = reuse_R and self.holds_R_of(W, Hs)     # left in the buffer by `energy(keep_R=True)` for these very W, H
+        R = self._R_for(n)                              # (clears the token: H changes below)
+        if not have_R:
+            R = self.reconstruct(W, Hs, out=R)
         p, Hs = self._h_problem(Hs)
         G_ptr, Gsum_ptr = None, None
         lam, lam_cross = 0.0, 0.0

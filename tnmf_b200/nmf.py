@@ -103,6 +103,8 @@ class TransformInvariantNMF:
         self._n_global = None
         self._n_local_max = None
         self._grad = None           # stacked (neg, pos) W-gradient buffer, the all-reduce payload
+        self._R_current = False     # the backend's R buffer holds reconstruct(W, H) of the current W and H (left there by
+                                    # an energy evaluation): the next H update starts from it instead of reconstructing
         self._shuffle_idx = None    # kept for interface parity; the reference never shuffles
 
     # ---------------------------------------------------------------------------------------------
@@ -140,8 +142,12 @@ class TransformInvariantNMF:
         return self._backend.reconstruct(self._W, self._H)
 
     def energy_device(self) -> torch.Tensor:
-        """0.5*||V-R||^2 over all samples of all ranks as a device-resident double (no host sync)."""
-        e = self._backend.energy(self._V, self._W, self._H)
+        """0.5*||V-R||^2 over all samples of all ranks as a device-resident double (no host sync).  The reconstruction it
+        is computed from stays in the backend's R buffer: it is the one the next H update opens with, so an energy read
+        in every iteration (a progress callback, the INFO log line of tnmf/TransformInvariantNMF.py:346) costs no third
+        reconstruction per iteration."""
+        e = self._backend.energy(self._V, self._W, self._H, keep_R=self._fused)
+        self._R_current = self._fused
         return self._sharding.sum_scalar(e)
 
     def _energy_function(self) -> float:
@@ -162,10 +168,12 @@ class TransformInvariantNMF:
         if normalization_axes is not None:
             self._backend.normalize(arr, axis=normalization_axes)
 
-    def _update_H(self, s: slice = sliceNone, sparsity: float = 0., inhibition: float = 0., cross_inhibition: float = 0.):
+    def _update_H(self, s: slice = sliceNone, sparsity: float = 0., inhibition: float = 0., cross_inhibition: float = 0.,
+                  reuse_R: bool = False):
+        self._R_current = False
         if self._fused:
             self._backend.update_H(self._V, self._W, self._H, s, sparsity, inhibition, cross_inhibition,
-                                   self._inhibition_kernels_1D, self.eps)
+                                   self._inhibition_kernels_1D, self.eps, reuse_R=reuse_R and s is sliceNone)
             return
         # reference call sequence, tnmf/TransformInvariantNMF.py:246-271
         neg, pos = self._backend.reconstruction_gradient_H(self._V, self._W, self._H, s)
@@ -197,6 +205,7 @@ class TransformInvariantNMF:
         return self._sharding.sum_gradient(grad) if reduce else grad
 
     def _apply_W(self, grad: torch.Tensor):
+        self._R_current = False
         if self._fused:
             self._backend.apply_W_update(self._W, grad, self.eps)
         else:
@@ -209,12 +218,11 @@ class TransformInvariantNMF:
     # ---------------------------------------------------------------------------------------------
     # initialisation
     # ---------------------------------------------------------------------------------------------
-    @staticmethod
-    def _assert_non_negative(V):
-        if isinstance(V, torch.Tensor):
-            assert bool((V >= 0).all())
-        else:
-            assert np.all(V >= 0)
+    def _assert_non_negative(self):
+        """The facade's `assert V.min() >= 0` (tnmf/TransformInvariantNMF.py:326,404), evaluated on the device copy of this
+        rank's samples right after the upload was queued: a pass over a 50 MB host batch costs the host 5-30 ms (and a
+        single-threaded one under torchrun), the device 10 us."""
+        assert bool((self._backend.min_of_V() >= 0).item()), 'V must be non-negative'
 
     def _initialize_matrices(self, V, keep_W: bool):
         sh = self._sharding
@@ -244,6 +252,7 @@ class TransformInvariantNMF:
             self._n_global = int(V.shape[0])
             self._n_local_max = int(V.shape[0])
         fresh_W = not (keep_W and self._W is not None)
+        self._R_current = False
         self._W, self._H = self._backend.initialize(V, self.atom_shape, self.n_atoms, None if fresh_W else self._W,
                                                     self._axes_W_normalization, sample_range=sample_range)
         if sample_range is not None:
@@ -262,10 +271,10 @@ class TransformInvariantNMF:
                   keep_W: bool = False, sparsity_H: float = 0., inhibition_strength: float = 0.,
                   cross_atom_inhibition_strength: float = 0.,
                   progress_callback: Callable[['TransformInvariantNMF', int], bool] = None):
-        self._assert_non_negative(V)
         assert update_H or update_W
         assert sparsity_H >= 0 and inhibition_strength >= 0 and cross_atom_inhibition_strength >= 0
         self._initialize_matrices(V, keep_W)
+        self._assert_non_negative()
         step = self._batch_step(update_H, update_W, sparsity_H, inhibition_strength, cross_atom_inhibition_strength)
         for iteration in range(n_iterations):
             step()
@@ -282,11 +291,15 @@ class TransformInvariantNMF:
                     cross_inhibition: float = 0.):
         """Callable performing one batch iteration (tnmf/TransformInvariantNMF.py:334-345) on the current W/H/V:
         eagerly the first time, from CUDA graphs afterwards (see `cuda_graph`)."""
-        def front():            # everything before the collective
+        def front(reuse_R=False):       # everything before the collective
             if update_H:
-                self._update_H(sliceNone, sparsity, inhibition, cross_inhibition)
+                self._update_H(sliceNone, sparsity, inhibition, cross_inhibition, reuse_R=reuse_R)
             if update_W:
                 self._gradient_W(sliceNone, reduce=False)
+
+        def take_R():           # True once after an energy evaluation left the current reconstruction behind
+            have, self._R_current = self._R_current and update_H, False
+            return have and self._backend.holds_R_of(self._W, self._H)
 
         def back():             # the W update proper
             if update_W:
@@ -298,7 +311,7 @@ class TransformInvariantNMF:
 
         if not (self._cuda_graph and self._fused and self._H.is_cuda and self._H.shape[0] > 0):
             def eager():
-                front()
+                front(take_R())
                 reduce()
                 back()
             return eager
@@ -307,7 +320,7 @@ class TransformInvariantNMF:
         key = (bool(update_H), bool(update_W), float(sparsity), float(inhibition), float(cross_inhibition),
                tuple(self._H.shape), tuple(self._H.stride()))
         return _GraphedStep(self._backend, front, reduce, back, self._sharding, self._step_cache, key,
-                            (self._H, self._backend._device_V(self._V), self._W, self._grad))   # pylint: disable=protected-access
+                            (self._H, self._backend._device_V(self._V), self._W, self._grad), take_R)   # pylint: disable=protected-access
 
     # ---------------------------------------------------------------------------------------------
     # minibatch algorithms (tnmf/TransformInvariantNMF.py:350-504)
@@ -362,12 +375,12 @@ class TransformInvariantNMF:
                         n_epochs: int = 1000, sag_lambda: float = 0.2, keep_W: bool = False, sparsity_H: float = 0.,
                         inhibition_strength: float = 0., cross_atom_inhibition_strength: float = 0.,
                         progress_callback: Callable[['TransformInvariantNMF', int], bool] = None):
-        self._assert_non_negative(V)
         assert sparsity_H >= 0 and inhibition_strength >= 0 and cross_atom_inhibition_strength >= 0
         assert isinstance(algorithm, MiniBatchAlgorithm)
         # the reference's `algorithm in (5, 6, 7, 8)` is never true for an Enum, so the samples are never shuffled
         # (tnmf/TransformInvariantNMF.py:410-411); only the batch order is (algorithms 5-8)
         self._initialize_matrices(V, keep_W)
+        self._assert_non_negative()
         batches = equal_batch_slices(self._H.shape[0], self._n_local_max, batch_size)
         kw_h = dict(sparsity=sparsity_H, inhibition=inhibition_strength, cross_inhibition=cross_atom_inhibition_strength)
         stat = None
@@ -431,13 +444,15 @@ class _GraphedStep:
     kernels touch alive, re-captures when the backend had to replace one (`B200_Backend.buffers_epoch`), and the
     facade caches the graphs across fits for as long as all pointers repeat (`cache`)."""
 
-    def __init__(self, backend, front, reduce, back, sharding, cache: dict, key: tuple, tensors: tuple):
+    def __init__(self, backend, front, reduce, back, sharding, cache: dict, key: tuple, tensors: tuple, take_R=None):
         self._backend, self._front, self._reduce, self._back = backend, front, reduce, back
+        self._take_R = take_R if take_R is not None else (lambda: False)
         self._sharded = sharding.is_sharded
         self._one_graph = not self._sharded or sharding.capturable
         self._calls = 0
         self._cache, self._key, self._tensors = cache, key, tensors
         self._entry = None          # (graphs, launches per replay, buffers epoch, tensors kept alive)
+        self._entry_reuse = None    # the same iteration without its opening reconstruction (see `energy_device`)
 
     def _capture(self, fn):
         # capture_begin / capture_end on a side stream instead of the `torch.cuda.graph` context manager: the latter
@@ -462,43 +477,55 @@ class _GraphedStep:
         be = self._backend
         return self._key + tuple(t.data_ptr() for t in self._tensors) + be.buffer_pointers()
 
-    def _eager(self):
-        self._front()
+    def _eager(self, reuse_R=False):
+        self._front(reuse_R)
         self._reduce()
         self._back()
+
+    def _entry_for(self, reuse_R: bool):
+        """The captured graphs of the iteration (with or without its opening reconstruction), capturing them on first use."""
+        be = self._backend
+        name = '_entry_reuse' if reuse_R else '_entry'
+        entry = getattr(self, name)
+        if entry is None:
+            key = self._full_key() + (reuse_R,)
+            entry = self._cache.get(key)
+            if entry is None or entry[2] != be.buffers_epoch:
+                torch.cuda.current_stream(be.device).synchronize()
+                if self._one_graph:
+                    g, n = self._capture(lambda: self._eager(reuse_R))
+                    graphs = (g,)
+                else:
+                    (g0, n0), (g1, n1) = self._capture(lambda: self._front(reuse_R)), self._capture(self._back)
+                    graphs, n = (g0, g1), n0 + n1
+                while len(self._cache) >= 4:
+                    self._cache.pop(next(iter(self._cache)))
+                entry = (graphs, n, be.buffers_epoch, self._tensors + be.buffer_tensors(), key)
+                self._cache[key] = entry
+            setattr(self, name, entry)
+        return entry
 
     def __call__(self):
         self._calls += 1
         be = self._backend
+        reuse_R = self._take_R()
         if self._calls == 1 or be.kernel_events is not None:        # per-kernel timing needs eager launches
-            self._eager()
+            self._eager(reuse_R)
             return
-        if self._entry is not None and self._entry[2] != be.buffers_epoch:
-            self._cache.pop(self._entry[4], None)                   # a buffer moved under the captured pointers
-            self._entry = None
-            self._eager()
-            return
-        if self._entry is None:
-            key = self._full_key()
-            self._entry = self._cache.get(key)
-            if self._entry is None or self._entry[2] != be.buffers_epoch:
-                torch.cuda.current_stream(be.device).synchronize()
-                if self._one_graph:
-                    g, n = self._capture(self._eager)
-                    graphs = (g,)
-                else:
-                    (g0, n0), (g1, n1) = self._capture(self._front), self._capture(self._back)
-                    graphs, n = (g0, g1), n0 + n1
-                while len(self._cache) >= 4:
-                    self._cache.pop(next(iter(self._cache)))
-                self._entry = (graphs, n, be.buffers_epoch, self._tensors + be.buffer_tensors(), key)
-                self._cache[key] = self._entry
-        graphs = self._entry[0]
+        for name in ('_entry', '_entry_reuse'):
+            entry = getattr(self, name)
+            if entry is not None and entry[2] != be.buffers_epoch:
+                self._cache.pop(entry[4], None)                     # a buffer moved under the captured pointers
+                self._entry = self._entry_reuse = None
+                self._eager(reuse_R)
+                return
+        entry = self._entry_for(reuse_R)
+        graphs = entry[0]
         graphs[0].replay()
         if len(graphs) > 1:
             self._reduce()
             graphs[1].replay()
-        be.launches += self._entry[1]
+        be.launches += entry[1]
 
 
 class _SubsampleFeeder:
