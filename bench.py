@@ -353,6 +353,7 @@ def run_b200(args, w):
     if sampler:
         sampler.start()
     launches0 = be.launches
+    peer_active = nmf._peer is not None                                  # pylint: disable=protected-access
     t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -506,7 +507,9 @@ def run_b200(args, w):
         'data': 'synthetic',
         'config': {'workload': f'{args.workload}: {w["text"]}', 'algorithm': 'batch MU (H update, W update)',
                    'samples_per_gpu': n_local, 'global_samples': world * n_local,
-                   'parallelism': f'sample-sharded x{world}, all-reduce of the W gradient' if world > 1 else 'single GPU',
+                   'parallelism': (f'sample-sharded x{world}, W gradient summed over the ranks '
+                                   + ('inside the W-update kernel over NVLink peer memory' if peer_active
+                                      else 'by an NCCL all-reduce')) if world > 1 else 'single GPU',
                    'kernel_path': be.kernel_families(), 'launch': 'CUDA graph replay of one iteration' if nmf._cuda_graph  # pylint: disable=protected-access
                    else 'eager launches',
                    'l2': 'working set (V, R, H) exceeds the 126 MB L2; no explicit flush'

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TNMF_ABI_VERSION 4
+#define TNMF_ABI_VERSION 5
 #define TNMF_MAX_SHIFT_DIMS 3
 
 /* element types */
@@ -160,6 +160,24 @@ int tnmf_gradient_w(const tnmf_problem *p, const void *V, const void *R, const v
  * Replaces TransformInvariantNMF._update_W's arithmetic, tnmf/TransformInvariantNMF.py:217-244, and
  * Backend.normalize, tnmf/backends/_Backend.py:75-77. */
 int tnmf_update_w(const tnmf_problem *p, void *W, const void *neg, const void *pos, double eps, void *stream);
+
+/* Multi-GPU W step in ONE kernel over NVLink peer memory: the stacked W gradient grad = [neg; pos] of this rank is summed
+ * with those of all `world` ranks and the W update above is applied to the sum - the all-reduce that the sample-sharded
+ * iteration needs (the sum over sample blocks of Cyclic_MU, tnmf/TransformInvariantNMF.py:457-465) fused with
+ * tnmf/TransformInvariantNMF.py:217-244 and Backend.normalize, tnmf/backends/_Backend.py:75-77.
+ *   buffers[r]   rank r's symmetric exchange buffer mapped into THIS process (tnmf_peer_buffer_bytes bytes each, zeroed
+ *                once before the first call, identical layout on every rank); every rank calls with the same world,
+ *   state        two zero-initialised uint32 in this rank's device memory (epoch, block counter),
+ * Collective: every rank must make the same sequence of calls.  The ranks add the same numbers in the same (rank) order
+ * in double, so W stays bit-identical on all ranks.  The call is stream-ordered and may be captured into a CUDA graph. */
+#define TNMF_MAX_PEERS 16
+typedef struct tnmf_peer_world {
+    int32_t world, rank;
+    void *buffers[TNMF_MAX_PEERS];
+} tnmf_peer_world;
+size_t tnmf_peer_buffer_bytes(const tnmf_problem *p, int32_t world);
+int tnmf_allreduce_update_w(const tnmf_problem *p, void *W, const void *grad, const tnmf_peer_world *peers, void *state,
+                            double eps, void *stream);
 
 /* arr[o,:,i] /= sum over the middle axis, for a tensor viewed as [outer, len, inner].
  * Replaces Backend.normalize, tnmf/backends/_Backend.py:75-77, for contiguous reduction axes. */

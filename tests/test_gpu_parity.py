@@ -700,6 +700,55 @@ def test_energy_callback_reuses_the_reconstruction(graph):
     assert launches[True] == launches[False] + 8 * (per_recon + 1) + foreign[0] - 6 * per_recon
 
 
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float64])
+def test_allreduce_update_w_kernel_against_plain_update(dtype):
+    """tnmf_allreduce_update_w (the W-gradient sum over ranks fused with the W update, NVLink peer memory) in ONE process:
+    the exchange buffer of 'rank 1' is a second buffer on the same device and its contribution is planted by hand (slot
+    [parity][1] of rank 0's buffer, flags = epoch) before rank 0's kernel runs.  Three consecutive calls (both slot
+    parities, the epoch counter) must equal tnmf_update_w on the summed gradient - bitwise: both round the double sum of
+    two floats once."""
+    import ctypes
+    from tnmf_b200 import B200_Backend, _lib
+    rng = np.random.default_rng(3)
+    M, C, A = 5, 3, (7, 6)
+    V = rng.random((2, C, 20, 24)).astype(np.float32 if dtype == torch.float32 else np.float64)
+    be = B200_Backend()
+    W, _ = be.initialize(V, A, M, None, (-2, -1))
+    lib, p = be._lib, be._problem(0, M)
+    world, pairs, avol = 2, M * C, A[0] * A[1]
+    count = pairs * avol
+    nbytes = int(lib.tnmf_peer_buffer_bytes(ctypes.byref(p), world))
+    esize = 4 if dtype == torch.float32 else 8
+    data_bytes = 2 * world * 2 * count * esize
+    flags_off = (data_bytes + 127) // 128 * 128
+    assert nbytes == flags_off + world * pairs * 4
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=be.device) for _ in range(world)]
+    pw = _lib.PeerWorld()
+    pw.world, pw.rank = world, 0
+    for r in range(world):
+        pw.buffers[r] = bufs[r].data_ptr()
+    state = torch.zeros(2, dtype=torch.int32, device=be.device)
+    data0 = bufs[0][:data_bytes].view(dtype).view(2, world, 2 * count)
+    flags0 = bufs[0][flags_off:].view(torch.int32).view(world, pairs)
+    W_ref = W.clone()
+    for call in range(1, 4):
+        g0 = torch.rand((2, M, C, *A), dtype=dtype, device=be.device) + 0.1
+        g1 = torch.rand((2, M, C, *A), dtype=dtype, device=be.device) + 0.1
+        data0[call & 1, 1] = g1.reshape(-1)             # what rank 1's kernel would have pushed
+        flags0[1] = call
+        _lib.check(lib.tnmf_allreduce_update_w(ctypes.byref(p), W.data_ptr(), g0.data_ptr(), ctypes.byref(pw),
+                                               state.data_ptr(), 1e-9, None), 'allreduce_update_w')
+        total = (g0.double() + g1.double()).to(dtype)
+        be.apply_W_update(W_ref, total, 1e-9)
+        torch.cuda.synchronize()
+        assert int(state[0].item()) == call and int(state[1].item()) == 0
+        assert torch.equal(W, W_ref), f'call {call}'
+        # rank 0 pushed its own gradient into slot [parity][0] of BOTH buffers and raised its flags everywhere
+        for b in bufs:
+            assert torch.equal(b[:data_bytes].view(dtype).view(2, world, 2 * count)[call & 1, 0], g0.reshape(-1))
+            assert bool((b[flags_off:].view(torch.int32).view(world, pairs)[0] == call).all())
+
+
 def test_empty_and_single_sample_batches():
     """Ragged minibatches: an empty slice contributes a zero W gradient, a short last batch is served."""
     rng = np.random.default_rng(7)

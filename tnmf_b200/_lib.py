@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.environ.get('TNMF_LIB_PATH') or os.path.join(HERE, 'libtnmf_b200.so')      # override: experiments only
 SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu', 'tma_kernels.cu', 'tc_hupd.cu', 'tc_gradw.cu', 'tc_recon.cu',
-           'tc_gradw_ts.cu', 'tc_recon_ts.cu', 'tc_hupd_ts.cu')
+           'tc_gradw_ts.cu', 'tc_recon_ts.cu', 'tc_hupd_ts.cu', 'peer_update_w.cu')
 # compiled once per atom-width chunk (-DTNMF_AXC=...): the register-tiled kernels
 CHUNKED_SOURCES = ('tiled_recon.cu', 'tiled_hupd.cu', 'tiled_gradw.cu', 'tma_recon.cu', 'tma_hupd.cu', 'tma_gradw.cu')
 CHUNKS = (4, 8, 12, 16)
@@ -30,7 +30,7 @@ MODES = {'valid': 0, 'full': 1, 'circular': 2}
 PATHS = {'auto': 0, 'generic': 1, 'tiled': 2, 'tma': 3, 'tc': 4}
 OP_RECONSTRUCT, OP_GRADIENT_H, OP_GRADIENT_W = 0, 1, 2
 TNMF_OK, TNMF_EINVAL, TNMF_EUNSUPPORTED, TNMF_EWORKSPACE, TNMF_ECUDA = 0, 1, 2, 3, 1000
-ABI_VERSION = 4
+ABI_VERSION = 5
 # tnmf_problem.flags (include/tnmf_b200.h)
 FLAG_NO_ROWS_VIEW, FLAG_ROWS_VIEW_ALWAYS = 1, 2
 FLAG_NO_TC_HUPD, FLAG_NO_TC_RECON, FLAG_NO_TC_GRADW, FLAG_NO_TC, FLAG_NO_TMA, FLAG_NO_TMEM_OPERAND = 4, 8, 16, 28, 32, 64
@@ -46,6 +46,14 @@ class Problem(ctypes.Structure):
         ('h_stride_n', ctypes.c_int64), ('h_stride_m', ctypes.c_int64),
         ('flags', ctypes.c_int32), ('reserved', ctypes.c_int32),
     ]
+
+
+MAX_PEERS = 16
+
+
+class PeerWorld(ctypes.Structure):
+    """Mirror of `struct tnmf_peer_world` (include/tnmf_b200.h)."""
+    _fields_ = [('world', ctypes.c_int32), ('rank', ctypes.c_int32), ('buffers', ctypes.c_void_p * MAX_PEERS)]
 
 
 _P = ctypes.POINTER(Problem)
@@ -66,6 +74,8 @@ SIGNATURES = {
     'tnmf_update_h': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _dbl, _vp, _dbl, _vp, _dbl, _vp, _sz, _vp]),
     'tnmf_gradient_w': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     'tnmf_update_w': (ctypes.c_int, [_P, _vp, _vp, _vp, _dbl, _vp]),
+    'tnmf_peer_buffer_bytes': (_sz, [_P, _i32]),
+    'tnmf_allreduce_update_w': (ctypes.c_int, [_P, _vp, _vp, ctypes.POINTER(PeerWorld), _vp, _dbl, _vp]),
     'tnmf_normalize': (ctypes.c_int, [_i32, _vp, _i64, _i64, _i64, _vp]),
     'tnmf_convolve_1d': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp]),
     'tnmf_sum_atoms': (ctypes.c_int, [_i32, _vp, _vp, _i64, _i64, _i64, _vp]),

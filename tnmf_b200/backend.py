@@ -574,6 +574,22 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         self.launches += self._n_launches(p, _lib.OP_GRADIENT_W)
         return out
 
+    def peer_exchange(self, sharding):
+        """Map the ranks' NVLink exchange buffers for `allreduce_update_W` (collective; None where unavailable)."""
+        from .distributed import PeerExchange
+        return PeerExchange.create(self._lib, self._problem(0, self.n_atoms), sharding, self.device)
+
+    def allreduce_update_W(self, W: torch.Tensor, grad: torch.Tensor, px, eps: float = 1.e-9) -> None:
+        """`apply_W_update` on the sum of `grad` over all ranks, in one kernel over NVLink peer memory (collective)."""
+        assert grad.is_contiguous() and W.is_contiguous()
+        p = self._problem(0, self.n_atoms)
+        with self._timed('update_w'):
+            _lib.check(self._lib.tnmf_allreduce_update_w(ctypes.byref(p), W.data_ptr(), grad.data_ptr(),
+                                                         ctypes.byref(px.world), px.state.data_ptr(), float(eps),
+                                                         _stream_ptr(self.device)), 'allreduce_update_w')
+        px.calls += 1
+        self.launches += 1
+
     def apply_W_update(self, W: torch.Tensor, grad: torch.Tensor, eps: float = 1.e-9) -> None:
         """W <- (W*neg)/(pos+eps), then per-(atom, channel) normalisation, in place
         (tnmf/TransformInvariantNMF.py:217-244, tnmf/backends/_Backend.py:75-77).  grad = stacked (neg, pos)."""

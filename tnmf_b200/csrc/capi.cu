@@ -425,6 +425,27 @@ int tnmf_update_w(const tnmf_problem *p, void *W, const void *neg, const void *p
     return update_w<double>(g, (double *)W, (const double *)neg, (const double *)pos, eps, st);
 }
 
+size_t tnmf_peer_buffer_bytes(const tnmf_problem *p, int32_t world) {
+    Geo g;
+    if (make_geo(p, g, false) || world < 1 || world > TNMF_MAX_PEERS) return 0;
+    return peer_buffer_bytes(g, p->dtype, world);
+}
+
+int tnmf_allreduce_update_w(const tnmf_problem *p, void *W, const void *grad, const tnmf_peer_world *peers, void *state,
+                            double eps, void *stream) {
+    Geo g;
+    int s = make_geo(p, g, false);
+    if (s) return s;
+    if (!W || !grad || !peers || !state) return TNMF_EINVAL;
+    if (peers->world < 1 || peers->world > TNMF_MAX_PEERS || peers->rank < 0 || peers->rank >= peers->world) return TNMF_EINVAL;
+    for (int r = 0; r < peers->world; ++r)
+        if (!peers->buffers[r]) return TNMF_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->dtype == TNMF_F32)
+        return allreduce_update_w<float>(g, p->dtype, (float *)W, (const float *)grad, peers, (unsigned *)state, eps, st);
+    return allreduce_update_w<double>(g, p->dtype, (double *)W, (const double *)grad, peers, (unsigned *)state, eps, st);
+}
+
 int tnmf_normalize(int32_t dtype, void *arr, int64_t outer, int64_t len, int64_t inner, void *stream) {
     if (!arr || outer < 1 || len < 1 || inner < 1) return TNMF_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;

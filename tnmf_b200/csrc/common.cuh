@@ -133,5 +133,11 @@ template <typename T> int convolve_axis(const T *in, T *out, long long outer, lo
                                         const double *taps, int n_taps, cudaStream_t st);
 template <typename T> int sum_atoms(const T *G, T *Gsum, long long n, long long m, long long inner, cudaStream_t st);
 int fp32_peak_probe(void *sink, int iterations, double *flops_out, cudaStream_t st);
+int sm_count_cached();
+
+// ---- implemented in peer_update_w.cu (all-reduce of the W gradient fused with the W update, NVLink peer memory) ------
+size_t peer_buffer_bytes(const Geo &g, int dtype, int world);
+template <typename T> int allreduce_update_w(const Geo &g, int dtype, T *W, const T *grad, const tnmf_peer_world *pw,
+                                             unsigned *state, double eps, cudaStream_t st);
 
 }  // namespace tnmf

@@ -5,6 +5,16 @@
 
 namespace tnmf {
 
+int sm_count_cached() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    }
+    return sms;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // energy: fixed-order sum of the per-block partials, E = 0.5 * sum          (tnmf/backends/_Backend.py:127-130)
 // ---------------------------------------------------------------------------------------------------------

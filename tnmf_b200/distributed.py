@@ -10,10 +10,14 @@ all-reduce per W update, and the W update itself runs redundantly - and bit-iden
 One process per GPU (torchrun); torch.distributed is the plumbing (NCCL over NVLink on the GPU box, gloo in the
 CPU tests).  Nothing here touches the arithmetic.
 """
+import ctypes
+import logging
 from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+_log = logging.getLogger(__name__)
 
 
 def shard_bounds(n_samples: int, world_size: int, rank: int) -> Tuple[int, int]:
@@ -85,3 +89,61 @@ class SampleSharding:
             dist.broadcast(tensor, src=src, group=self.group)
             self.collectives += 1
         return tensor
+
+
+class PeerExchange:
+    """Symmetric NVLink peer buffers for `tnmf_allreduce_update_w` (include/tnmf_b200.h): the all-reduce of the W gradient
+    fused with the W update in one kernel, instead of an NCCL all-reduce between two kernels.
+
+    Every rank allocates one exchange buffer with torch's symmetric-memory allocator and the ranks map each other's
+    buffers (`rendezvous`, a collective over the process group); the kernel then writes its gradient straight into the
+    peers' memory.  torch provides the memory and the handle exchange - plumbing; the exchange itself is the library's
+    kernel.  Construction is collective; `create` returns None (on every rank alike) where peer memory is not to be had -
+    a CPU process group, ranks sharing a device, more than 16 ranks, a driver without peer mappings - and the caller
+    keeps the NCCL all-reduce."""
+
+    def __init__(self, lib, problem, group, device, world: int, rank: int):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        nbytes = int(lib.tnmf_peer_buffer_bytes(ctypes.byref(problem), world))
+        if nbytes <= 0:
+            raise RuntimeError('tnmf_peer_buffer_bytes refused the problem')
+        self.buffer = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buffer.zero_()
+        self.handle = symm.rendezvous(self.buffer, dist.group.WORLD if group is None else group)
+        ptrs = [int(q) for q in self.handle.buffer_ptrs]
+        if len(ptrs) != world or int(self.handle.rank) != rank:
+            raise RuntimeError('symmetric-memory rendezvous disagrees with the process group')
+        self.world = _lib.PeerWorld()
+        self.world.world, self.world.rank = world, rank
+        for r, q in enumerate(ptrs):
+            self.world.buffers[r] = q
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)
+        self.calls = 0
+        torch.cuda.synchronize(device)
+
+    @staticmethod
+    def create(lib, problem, sharding: 'SampleSharding', device) -> Optional['PeerExchange']:
+        from . import _lib
+        sh = sharding
+        ok = sh.is_sharded and sh.capturable and sh.world_size <= _lib.MAX_PEERS and device.type == 'cuda'
+        if ok:
+            # one device per rank (the kernel of one rank waits for the kernels of the others: they must run concurrently)
+            mine = torch.tensor([device.index if device.index is not None else torch.cuda.current_device()],
+                                dtype=torch.int64, device=device)
+            every = [torch.empty_like(mine) for _ in range(sh.world_size)]
+            dist.all_gather(every, mine, group=sh.group)
+            ok = len({int(t.item()) for t in every}) == sh.world_size
+        px = None
+        if ok:
+            try:
+                px = PeerExchange(lib, problem, sh.group, device, sh.world_size, sh.rank)
+            except Exception as exc:  # pylint: disable=broad-except
+                _log.warning('NVLink peer exchange unavailable (%s): the W gradient goes through the NCCL all-reduce', exc)
+        if sh.is_sharded and sh.capturable:
+            # all or none: a rank that failed to map its peers must not leave the others waiting in the kernel
+            flag = torch.tensor([1 if px is not None else 0], dtype=torch.int32, device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=sh.group)
+            if int(flag.item()) == 0:
+                px = None
+        return px

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .backend import B200_Backend
-from .distributed import SampleSharding, equal_batch_slices
+from .distributed import PeerExchange, SampleSharding, equal_batch_slices
 
 sliceNone = slice(None)
 
@@ -53,6 +53,10 @@ class TransformInvariantNMF:
     fused : bool, default True
         False drives the backend through the reference interface only (reconstruction_gradient_H/W + the
         update arithmetic as tensor operations), i.e. exactly the call sequence of the stock facade.
+    peer_exchange : bool, default True
+        Sharded runs over NCCL only: sum the W gradient over the ranks inside the W-update kernel, through NVLink peer
+        memory (`tnmf_allreduce_update_w`), instead of an NCCL all-reduce between the W gradient and the W update.  Falls
+        back to the all-reduce where peer memory cannot be mapped.
     cuda_graph : bool, default True
         Batch algorithm only: after one eager iteration the kernel launches of an iteration are captured into CUDA
         graphs (everything up to the all-reduce of the W gradient, and the W update after it) and replayed, which
@@ -63,7 +67,8 @@ class TransformInvariantNMF:
     def __init__(self, n_atoms: int, atom_shape: Tuple[int, ...], inhibition_range: Union[int, Tuple[int, ...]] = None,
                  backend: str = 'b200', logger: logging.Logger = None, verbose: int = 0,
                  distributed: Optional[bool] = None, process_group=None, input_is_local_shard: bool = False,
-                 fused: bool = True, cuda_graph: bool = True, equal_shards: bool = False, **kwargs):
+                 fused: bool = True, cuda_graph: bool = True, equal_shards: bool = False, peer_exchange: bool = True,
+                 **kwargs):
         self.atom_shape = tuple(atom_shape)
         if inhibition_range is None:
             self._inhibition_range = tuple(a - 1 for a in self.atom_shape)   # just covers the atom
@@ -91,6 +96,9 @@ class TransformInvariantNMF:
         self._input_is_local = bool(input_is_local_shard)
         self._equal_shards = bool(equal_shards)
         self._counts_for = None
+        self._use_peer = bool(peer_exchange) and self._fused
+        self._peer = None           # PeerExchange of the current dictionary shape (None: NCCL all-reduce)
+        self._peer_for = None
         self._step_cache = None     # (key, _GraphedStep): CUDA graphs survive across fits while every buffer stays put
 
         self._logger = logger if logger is not None else logging.getLogger(self.__class__.__name__)
@@ -212,8 +220,16 @@ class TransformInvariantNMF:
             self._multiplicative_update(self._W, grad[0].clone(), grad[1].clone(),
                                         normalization_axes=self._axes_W_normalization)
 
+    def _reduce_apply_W(self, grad: torch.Tensor):
+        """Sum `grad` over the ranks and apply the W update: one kernel over NVLink peer memory, or all-reduce + update."""
+        if self._peer is not None:
+            self._R_current = False
+            self._backend.allreduce_update_W(self._W, grad, self._peer, self.eps)
+        else:
+            self._apply_W(self._sharding.sum_gradient(grad))
+
     def _update_W(self, s: slice = sliceNone):
-        self._apply_W(self._gradient_W(s))
+        self._reduce_apply_W(self._gradient_W(s, reduce=False))
 
     # ---------------------------------------------------------------------------------------------
     # initialisation
@@ -263,6 +279,10 @@ class TransformInvariantNMF:
             sh.broadcast(self._W, 0)
         if self._grad is None or self._grad.shape[1:] != self._W.shape or self._grad.dtype != self._W.dtype:
             self._grad = torch.empty((2, *self._W.shape), dtype=self._W.dtype, device=self._W.device)
+        if self._use_peer and sh.is_sharded and self._peer_for != (tuple(self._W.shape), self._W.dtype):
+            # collective (every rank gets here with the same dictionary shape): map the peers' exchange buffers once
+            self._peer_for = (tuple(self._W.shape), self._W.dtype)
+            self._peer = self._backend.peer_exchange(sh)
 
     # ---------------------------------------------------------------------------------------------
     # batch algorithm (tnmf/TransformInvariantNMF.py:282-348)
@@ -301,12 +321,14 @@ class TransformInvariantNMF:
             have, self._R_current = self._R_current and update_H, False
             return have and self._backend.holds_R_of(self._W, self._H)
 
-        def back():             # the W update proper
-            if update_W:
+        def back():             # the W update proper (with the sum over ranks inside when the peers are mapped)
+            if update_W and self._peer is not None:
+                self._reduce_apply_W(self._grad)
+            elif update_W:
                 self._apply_W(self._grad)
 
         def reduce():
-            if update_W:
+            if update_W and self._peer is None:
                 self._sharding.sum_gradient(self._grad)
 
         if not (self._cuda_graph and self._fused and self._H.is_cuda and self._H.shape[0] > 0):
@@ -346,7 +368,7 @@ class TransformInvariantNMF:
             for b in batches:
                 self._update_H(b, **kw_h)
                 acc = self._blend(acc, self._gradient_W(b, reduce=False), 1.)
-            self._apply_W(self._sharding.sum_gradient(acc))
+            self._reduce_apply_W(acc)
         elif algorithm == MiniBatchAlgorithm.ASG_MU:               # :467-472
             for b in self._shuffled(batches):
                 self._update_H(b, **kw_h)
