@@ -117,6 +117,11 @@ int tnmf_uses_tiled_path(const tnmf_problem *p);
  * the forced `path` cannot serve it. */
 int tnmf_kernel_family(const tnmf_problem *p, int op);
 
+/* Name of the hot kernel that serves operation `op` of this problem ("recon_ts_kernel", "hupd_tma_kernel", ...; the
+ * __global__ function an ncu launch list shows), or "none" like tnmf_kernel_family's -1.  Static string.  Diagnostics:
+ * parity tests and bench.py record which kernel they exercised. */
+const char *tnmf_kernel_name(const tnmf_problem *p, int op);
+
 /* How many kernels one call of operation `op` launches for this problem (the fused / unfused H operations alike), or -1
  * like tnmf_kernel_family.  Bookkeeping for callers that report launch counts (bench.py's "gpu_launches"). */
 int tnmf_launch_count(const tnmf_problem *p, int op);

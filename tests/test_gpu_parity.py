@@ -560,6 +560,47 @@ def test_tc_reconstruct_vs_oracle(case, mode, tmem):
     _close(be.partial_reconstruct(Wd, Hd, M - 1), orc.reconstruct(W64[M - 1:], H64[:, M - 1:], mode), 2e-5)
 
 
+OS_CASES = [
+    # N, C, M, D, A: narrow atoms, many atoms - the activation-row ring of recon_ts does not fit tensor memory
+    (2, 1, 32, (40, 50), (15, 15)),     # cfg3 atoms: 16 accumulator slots, window of 15, four operand stages
+    (3, 1, 24, (100, 37), (9, 9)),      # tall samples: the accumulator ring wraps many times; 24 atoms = 3 K steps
+    (2, 2, 32, (30, 70), (8, 7)),       # two channels in one 16-column slot
+    (40, 1, 17, (20, 130), (15, 3)),    # more work units than SMs; 17 atoms padded to 24
+    (2, 2, 30, (64, 40), (7, 12)),      # 32-column slots: ring of 10, three stages
+    (1, 1, 32, (15, 15), (15, 15)),     # atom as large as the sample ('full': one activation feeds every output row)
+]
+
+
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+@pytest.mark.parametrize('case', range(len(OS_CASES)))
+def test_tc_reconstruct_narrow_atoms_vs_oracle(case, mode):
+    """recon_os_kernel (source-row stationary, output rows as a ring of accumulators in tensor memory; BASELINE config 3's
+    reconstruction) against the oracle: R, the fused energy, a minibatch slice, bitwise repeatability (one issuing warp:
+    the truncating tensor-core accumulation runs in program order)."""
+    N, C, M, D, A = OS_CASES[case]
+    rng = np.random.default_rng(700 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    R = be.reconstruct(Wd, Hd)
+    assert be.kernel_names()['reconstruct'] == 'recon_os_kernel', be.kernel_names()
+    ref = orc.reconstruct(W64, H64, mode)
+    _close(R, ref, 2e-5)
+    assert torch.equal(be.reconstruct(Wd, Hd), R)
+    assert np.isclose(be.reconstruction_energy(V, Wd, Hd), orc.reconstruction_energy(V64, W64, H64, mode), rtol=2e-5)
+    if N > 2:
+        _close(be.reconstruct(Wd, Hd[1:N - 1]), ref[1:N - 1], 2e-5)
+    # 'auto' takes the same kernel for these shapes when the batch fills the tiles
+    be2, Wd2, Hd2 = _backend(V, W, H, mode, 'auto')
+    nu, km = C * A[1], (M + 7) // 8 * 8
+    useful = nu / ((nu + 15) // 16 * 16) * M / km * (128 - (A[1] - 1)) / 128      # share of every MMA that is real work
+    if N * D[1] >= 128 and A[0] >= 3 and useful >= 0.5:
+        _close(be2.reconstruct(Wd2, Hd2), ref, 2e-5)
+        assert be2.kernel_names()['reconstruct'] == 'recon_os_kernel', be2.kernel_names()
+
+
 @pytest.mark.parametrize('seed', range(10))
 def test_tc_kernels_vs_generic_on_random_shapes(seed):
     """Randomly drawn supported shapes (ragged tiles, rows far beyond one trip round the TMEM / activation rings, atom

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.environ.get('TNMF_LIB_PATH') or os.path.join(HERE, 'libtnmf_b200.so')      # override: experiments only
 SOURCES = ('capi.cu', 'generic_kernels.cu', 'elementwise.cu', 'tiled_kernels.cu', 'tma_kernels.cu', 'tc_hupd.cu', 'tc_gradw.cu', 'tc_recon.cu',
-           'tc_gradw_ts.cu', 'tc_recon_ts.cu', 'tc_hupd_ts.cu', 'peer_update_w.cu')
+           'tc_gradw_ts.cu', 'tc_recon_ts.cu', 'tc_hupd_ts.cu', 'tc_recon_os.cu', 'peer_update_w.cu')
 # compiled once per atom-width chunk (-DTNMF_AXC=...): the register-tiled kernels
 CHUNKED_SOURCES = ('tiled_recon.cu', 'tiled_hupd.cu', 'tiled_gradw.cu', 'tma_recon.cu', 'tma_hupd.cu', 'tma_gradw.cu')
 CHUNKS = (4, 8, 12, 16)
@@ -67,6 +67,7 @@ SIGNATURES = {
     'tnmf_workspace_bytes': (_sz, [_P]),
     'tnmf_uses_tiled_path': (ctypes.c_int, [_P]),
     'tnmf_kernel_family': (ctypes.c_int, [_P, ctypes.c_int]),
+    'tnmf_kernel_name': (ctypes.c_char_p, [_P, ctypes.c_int]),
     'tnmf_launch_count': (ctypes.c_int, [_P, ctypes.c_int]),
     'tnmf_reconstruct': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _sz, _vp]),
     'tnmf_reconstruct_energy': (ctypes.c_int, [_P, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),

@@ -306,6 +306,21 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
                 for op, code in (('reconstruct', _lib.OP_RECONSTRUCT), ('update_h', _lib.OP_GRADIENT_H),
                                  ('gradient_w', _lib.OP_GRADIENT_W))}
 
+    def kernel_names(self, n: Optional[int] = None) -> dict:
+        """The hot kernel (__global__ function name, as an ncu launch list shows it) behind each operation; arguments as
+        for `kernel_families`."""
+        if n is None:
+            p = self._last_h_problem
+        else:
+            shape = (int(n), self.n_atoms, *self._transform_shape)
+            pad = self._h_padding(shape)
+            hsm = int(np.prod(shape[2:-1], dtype=np.int64)) * (shape[-1] + pad)
+            p = self._problem(int(n), self.n_atoms, self.n_atoms * hsm, hsm,
+                              (shape[-1] + pad) if pad and len(self.atom_shape) >= 2 else 0)
+        return {op: self._lib.tnmf_kernel_name(ctypes.byref(p), code).decode()
+                for op, code in (('reconstruct', _lib.OP_RECONSTRUCT), ('update_h', _lib.OP_GRADIENT_H),
+                                 ('gradient_w', _lib.OP_GRADIENT_W))}
+
     def uses_tiled_kernels(self, n: Optional[int] = None) -> bool:
         p = self._problem(self.n_samples if n is None else n, self.n_atoms)
         return bool(self._lib.tnmf_uses_tiled_path(ctypes.byref(p)))

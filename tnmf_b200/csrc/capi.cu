@@ -113,6 +113,27 @@ bool tc_recon_ts_worthwhile(const Geo &g) {
     return useful >= 0.5 && (long long)g.N * g.D[2] >= 128 && g.A[1] >= 3;
 }
 
+// The reconstruction for narrow atoms (tc_recon_os.cu: output rows as a ring of accumulators in tensor memory, one MMA of
+// N = A_y * roundup(C * A_x, 16) per source row and K step) serves what the activation-ring kernel cannot hold - one
+// channel, many atoms (cfg3).  'auto' takes it when at least half of every MMA is useful work.
+bool tmem_operand_recon_os(const Geo &g, int dtype) {
+    return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_recon_os_supported(g, dtype);
+}
+bool tc_recon_os_worthwhile(const Geo &g) {
+    if (g.flags & TNMF_FLAG_NO_TC_RECON) return false;
+    const int nu = g.C * g.A[2], np = (nu + 15) / 16 * 16, km = (g.M + 7) / 8 * 8;
+    const double useful = ((double)nu / np) * ((double)g.M / km) * (double)(128 - (g.A[2] - 1)) / 128.0;
+    return useful >= 0.5 && (long long)g.N * g.D[2] >= 128 && g.A[1] >= 3;
+}
+// which of the three tensor-core reconstructions serves a problem whose family is TNMF_PATH_TC
+enum { RECON_TS = 0, RECON_OS = 1, RECON_SS = 2 };
+int tc_recon_variant(const tnmf_problem *p, const Geo &g) {
+    const bool forced = p->path == TNMF_PATH_TC;
+    if (tmem_operand_recon(g, p->dtype) && (forced || tc_recon_ts_worthwhile(g))) return RECON_TS;
+    if (tmem_operand_recon_os(g, p->dtype) && (forced || tc_recon_os_worthwhile(g))) return RECON_OS;
+    return RECON_SS;
+}
+
 // Kernel family serving operation `op`: TMA where eligible, else the cp.async tiled kernels, else the generic ones;
 // a forced family that cannot serve the problem is an error.
 int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
@@ -123,6 +144,9 @@ int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
         return TNMF_PATH_TC;
     if (op == TNMF_OP_RECONSTRUCT && tmem_operand_recon(g, p->dtype) &&
         (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_ts_worthwhile(g))))
+        return TNMF_PATH_TC;
+    if (op == TNMF_OP_RECONSTRUCT && tmem_operand_recon_os(g, p->dtype) &&
+        (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_os_worthwhile(g))))
         return TNMF_PATH_TC;
     if (op == TNMF_OP_RECONSTRUCT && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_worthwhile(g))) &&
         tc_recon_supported(g, p->dtype))
@@ -224,6 +248,27 @@ int tnmf_kernel_family(const tnmf_problem *p, int op) {
     return choose_family(p, g, op, &err);
 }
 
+const char *tnmf_kernel_name(const tnmf_problem *p, int op) {
+    Geo g;
+    if (make_geo(p, g) || op < TNMF_OP_RECONSTRUCT || op > TNMF_OP_GRADIENT_W) return "none";
+    int err;
+    const int f = choose_family(p, g, op, &err);
+    static const char *const names[3][4] = {
+        {"generic_reconstruct_kernel", "tiled::recon_kernel", "recon_tma_kernel", ""},
+        {"generic_gradient_h_kernel", "tiled::hupd_kernel", "hupd_tma_kernel", ""},
+        {"generic_gradient_w_kernel", "tiled::gradw_kernel", "gradw_tma_kernel", ""}};
+    if (f == TNMF_PATH_GENERIC) return names[op][0];
+    if (f == TNMF_PATH_TILED) return names[op][1];
+    if (f == TNMF_PATH_TMA) return names[op][2];
+    if (f != TNMF_PATH_TC) return "none";
+    if (op == TNMF_OP_RECONSTRUCT) {
+        const int v = tc_recon_variant(p, g);
+        return v == RECON_TS ? "recon_ts_kernel" : v == RECON_OS ? "recon_os_kernel" : "recon_tc_kernel";
+    }
+    if (op == TNMF_OP_GRADIENT_H) return tmem_operand_hupd(g, p->dtype) ? "hupd_ts_kernel" : "hupd_tc_kernel";
+    return tmem_operand_gradw(g, p->dtype) ? "gradw_ts_kernel" : "gradw_tc_kernel";
+}
+
 int tnmf_launch_count(const tnmf_problem *p, int op) {
     Geo g;
     if (make_geo(p, g)) return -1;
@@ -247,10 +292,14 @@ int tnmf_reconstruct(const tnmf_problem *p, const void *W, const void *H, void *
     cudaStream_t st = (cudaStream_t)stream;
     int family = choose_family(p, g, TNMF_OP_RECONSTRUCT, &s);
     if (s) return s;
-    if (family == TNMF_PATH_TC && tmem_operand_recon(g, p->dtype))
-        return tc_reconstruct_ts(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
-    if (family == TNMF_PATH_TC)
+    if (family == TNMF_PATH_TC) {
+        const int variant = tc_recon_variant(p, g);
+        if (variant == RECON_TS)
+            return tc_reconstruct_ts(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
+        if (variant == RECON_OS)
+            return tc_reconstruct_os(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
         return tc_reconstruct(g, (const float *)W, (const float *)H, (float *)R, nullptr, nullptr, nullptr, st);
+    }
     if (family == TNMF_PATH_TMA && (!aligned16(H) || !workspace)) {
         if (p->path == TNMF_PATH_TMA) return workspace ? TNMF_EUNSUPPORTED : TNMF_EWORKSPACE;
         family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
@@ -289,8 +338,10 @@ int tnmf_reconstruct_energy(const tnmf_problem *p, const void *V, const void *W,
         family = tiled_supported(g, p->dtype) ? TNMF_PATH_TILED : TNMF_PATH_GENERIC;
     }
     const bool tiled = family == TNMF_PATH_TILED;
-    if (family == TNMF_PATH_TC && tmem_operand_recon(g, p->dtype)) {
+    if (family == TNMF_PATH_TC && tc_recon_variant(p, g) == RECON_TS) {
         s = tc_reconstruct_ts(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials, st);
+    } else if (family == TNMF_PATH_TC && tc_recon_variant(p, g) == RECON_OS) {
+        s = tc_reconstruct_os(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials, st);
     } else if (family == TNMF_PATH_TC) {
         s = tc_reconstruct(g, (const float *)W, (const float *)H, (float *)R, (const float *)V, partials, &n_partials, st);
     } else if (family == TNMF_PATH_TMA) {

@@ -123,6 +123,12 @@ int tc_recon_ts_partials(const Geo &g);
 int tc_reconstruct_ts(const Geo &g, const float *W, const float *H, float *R, const float *V, double *energy_partials,
                       int *n_partials, cudaStream_t st);
 
+// ---- implemented in tc_recon_os.cu (tcgen05 3xTF32, narrow atoms: output-row accumulator ring in tensor memory) -------
+bool tc_recon_os_supported(const Geo &g, int dtype);
+int tc_recon_os_partials(const Geo &g);
+int tc_reconstruct_os(const Geo &g, const float *W, const float *H, float *R, const float *V, double *energy_partials,
+                      int *n_partials, cudaStream_t st);
+
 // ---- implemented in elementwise.cu ----------------------------------------------------------------------
 int finish_energy(const double *partials, int n, double *energy, cudaStream_t st);
 template <typename T> int finish_gradient_w(const T *partials, int n_partials, long long count, T *neg, T *pos,
