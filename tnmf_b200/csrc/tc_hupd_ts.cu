@@ -45,6 +45,7 @@ struct Plan {
     int KPL, KP, ksteps;            // C*AX, padded to a multiple of 8
     int TXP, RW, raw_floats, nraw;
     int RS, pos_col0, a_col0;       // ring slots, first TMEM column of the pos ring / of the operand buffers
+    int shared_ab;                  // 1: V and R take turns in ONE operand buffer (the rings leave room for one only)
     int w_floats;
     int tiles, rblocks, rows_per_block;
     long long units;
@@ -71,7 +72,14 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.ksteps = p.KP / 8;
     p.RS = (512 - 4 * p.KP) / (2 * kNB);
     if (p.RS > kRingMax) p.RS = kRingMax;
-    if (p.RS < g.AY) return false;
+    if (p.RS < g.AY) {
+        // one operand buffer for both tensors (cfg3: 15 atom rows -> 480 ring columns + 2 * KP = 512): the V and R stages
+        // alternate anyway; what is lost is the expansion of one tensor running under the other tensor's MMAs
+        p.RS = (512 - 2 * p.KP) / (2 * kNB);
+        if (p.RS > kRingMax) p.RS = kRingMax;
+        if (p.RS < g.AY) return false;
+        p.shared_ab = 1;
+    }
     p.pos_col0 = p.RS * kNB;
     p.a_col0 = 2 * p.RS * kNB;
     p.w_floats = 2 * g.AY * kNB * p.KP;
@@ -170,7 +178,8 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
         const int t128 = tid & 127;
         const float *src_t = X ? a.R : a.V;
         float *raw_x = raw + (size_t)X * 2 * p.raw_floats;
-        const unsigned t_lane = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(p.a_col0 + X * 2 * KP);
+        const unsigned t_lane = tmem_base + ((unsigned)(quarter * 32) << 16) +
+                                (unsigned)(p.a_col0 + (p.shared_ab ? 0 : X * 2 * KP));
         const long long plane = (long long)g.DY * g.DX;
         const int raw_count = C * RW;
         unsigned stage = 0, buf = 0;
@@ -215,7 +224,14 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
 #pragma unroll
                 for (int k = 0; k < KPT; ++k) v[k] = k < p.KPL ? pw[p.koff[k]] : 0.f;
                 // the window is in registers before the operand buffer is free: only the split and the stores wait for it
-                if (stage) TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[X], (stage - 1u) & 1u, 20));
+                if (!p.shared_ab) {
+                    if (stage) TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[X], (stage - 1u) & 1u, 20));
+                } else if (X) {
+                    // one buffer, used in the order V(0) R(0) V(1) R(1) ...: R(s) may be written when the MMAs of V(s) are done
+                    TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[0], stage & 1u, 20));
+                } else if (stage) {
+                    TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[1], (stage - 1u) & 1u, 20));     // V(s): after R(s - 1)
+                }
                 tc_fence_after();
 #ifdef TNMF_TC_PROFILE
                 const long long t_e = clock64();
@@ -369,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
         const unsigned w_lo_word = __shfl_sync(0xffffffffu, (smem_u32(w_lo) >> 4) + ((lbo_b >> 4) << 16), 0);
         const unsigned b_step16 = (2 * lbo_b) >> 4;
         const unsigned ring0 = tmem_u + (unsigned)(X ? p.pos_col0 : 0);
-        const unsigned ta_hi = tmem_u + (unsigned)(p.a_col0 + X * 2 * KP), ta_lo = ta_hi + (unsigned)KP;
+        const unsigned ta_hi = tmem_u + (unsigned)(p.a_col0 + (p.shared_ab ? 0 : X * 2 * KP)), ta_lo = ta_hi + (unsigned)KP;
         const int ksteps = p.ksteps;
         unsigned stage = 0;
         int slot_new = 0, slot_a = 0, slot_done = 0;            // slot of the next row to enter / of the window's first row /
