@@ -56,8 +56,8 @@ struct Plan {
     int KS, n_sub, n_astages, a_col0, NA;
     int RS, NRr, ring_floats;       // logical ring slots, physical ring rows (16 per slot, RS + AY - 1 slots: the first
                                     // AY - 1 slots are mirrored behind the last one), floats of ONE of the hi / lo halves
-    int tiles, rblocks, rows_per_block;
-    long long units;
+    int tiles;
+    long long total, quota, units;  // tile-rows of the problem, tile-rows per CTA, grid * (most segments of a CTA)
     int grid;
     size_t smem;
 };
@@ -103,18 +103,17 @@ bool make_plan(const Geo2 &g, Plan &p) {
     const long long cols = (long long)g.N * p.TXP;
     if (cols <= 0 || cols >= (1ll << 31) - kCT) return false;
     p.tiles = (int)((cols + kCT - 1) / kCT);
+    // Work split: the (tile, row) space is cut into `grid` equal LINEAR ranges, one per CTA (a range is a few row segments
+    // of consecutive tiles) - every SM gets the same number of rows whatever the number of tiles (cfg2: 138 / 145 / 276
+    // tiles on 148 SMs left 7 - 10 % of the SMs idle with whole-tile units).  A segment boundary costs AY - 1 extra source
+    // rows, and there are at most two per CTA.
     const int sms = tma::sm_count();
-    double best = -1;
-    for (int rb = 1; rb <= g.TY && rb <= 64; ++rb) {
-        const int rows = ceil_div(g.TY, rb);
-        if (ceil_div(g.TY, rows) != rb) continue;
-        const long long units = (long long)p.tiles * rb;
-        const double waves = (double)((units + sms - 1) / sms);
-        const double cost = waves * (rows + 0.5 * (g.AY - 1) + 1.0);
-        if (best < 0 || cost < best * 0.999) { best = cost; p.rblocks = rb; p.rows_per_block = rows; }
-    }
-    p.units = (long long)p.tiles * p.rblocks;
-    p.grid = (int)(p.units < sms ? p.units : sms);
+    p.total = (long long)p.tiles * g.TY;
+    p.quota = (p.total + sms - 1) / sms;
+    const long long min_quota = g.TY < 8 ? g.TY : 8;
+    if (p.quota < min_quota) p.quota = min_quota;
+    p.grid = (int)((p.total + p.quota - 1) / p.quota);
+    p.units = (long long)p.grid * ((p.quota + g.TY - 2) / g.TY + 1);
     return true;
 }
 
@@ -122,11 +121,15 @@ struct Unit {
     int tile, ty0, ty1, r_lo, r_hi;
 };
 __device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan &p) {
+    // unit u = segment u / grid of CTA u % grid (gridDim.x == p.grid); empty (ty0 == ty1) past the CTA's last segment
     Unit w;
-    const int rb = (int)(u / p.tiles);
-    w.tile = (int)(u - (long long)rb * p.tiles);
-    w.ty0 = rb * p.rows_per_block;
-    w.ty1 = min(g.TY, w.ty0 + p.rows_per_block);
+    const long long b = u % p.grid, k = u / p.grid;
+    const long long lo = b * p.quota, hi = min(lo + p.quota, p.total);
+    w.tile = (int)(lo / g.TY + k);
+    const long long t0 = (long long)w.tile * g.TY;
+    const long long s0 = max(lo, t0), s1 = min(hi, t0 + g.TY);
+    w.ty0 = s1 > s0 ? (int)(s0 - t0) : 0;
+    w.ty1 = s1 > s0 ? (int)(s1 - t0) : 0;
     w.r_lo = max(0, w.ty0 - g.offy);
     w.r_hi = min(g.DY - 1, w.ty1 - 1 - g.offy + g.AY - 1);
     return w;
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
         unsigned wraps = 0;                                     // the row loop (they were most of its critical path)
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.ty0 >= w.ty1) break;                            // past this CTA's last segment
             // source element of every raw slot (q = tid + 256 e -> tensor, channel, position) in row 0, or -1: zero
             long long roff[kRawMax];
             int rdst[kRawMax];
@@ -364,6 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
         };
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.ty0 >= w.ty1) break;                            // past this CTA's last segment
             rows_done += w.r_hi - w.r_lo + 1;
         }
         const int n_epochs = (rows_done + kEpoch - 1) / kEpoch;
@@ -406,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
 #endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.ty0 >= w.ty1) break;                            // past this CTA's last segment
             int next_new = w.ty0, next_out = w.ty0, win0 = w.ty0;
             slot_a = slot_new;                                      // the unit's first activation row enters here
             for (int r = w.r_lo; r <= w.r_hi; ++r) {

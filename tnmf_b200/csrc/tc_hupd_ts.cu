@@ -47,8 +47,8 @@ struct Plan {
     int RS, pos_col0, a_col0;       // ring slots, first TMEM column of the pos ring / of the operand buffers
     int shared_ab;                  // 1: V and R take turns in ONE operand buffer (the rings leave room for one only)
     int w_floats;
-    int tiles, rblocks, rows_per_block;
-    long long units;
+    int tiles;
+    long long total, quota, units;  // tile-rows of the problem, tile-rows per CTA, grid * (most segments of a CTA)
     int grid;
     size_t smem;
     int koff[64];                   // k = (c, ax) -> c * RW + ax: offset of the tap in a raw row (kernel parameters live in
@@ -94,18 +94,17 @@ bool make_plan(const Geo2 &g, Plan &p) {
     const long long cols = (long long)g.N * p.TXP;
     if (cols <= 0 || cols >= (1ll << 31) - kTile) return false;
     p.tiles = (int)((cols + kTile - 1) / kTile);
+    // Work split: the (tile, row) space is cut into `grid` equal LINEAR ranges, one per CTA (a range is a few row segments
+    // of consecutive tiles) - every SM gets the same number of rows whatever the number of tiles (cfg2: 138 / 145 / 276
+    // tiles on 148 SMs left 7 - 10 % of the SMs idle with whole-tile units).  A segment boundary costs AY - 1 extra source
+    // rows, and there are at most two per CTA.
     const int sms = tma::sm_count();
-    double best = -1;
-    for (int rb = 1; rb <= g.TY && rb <= 64; ++rb) {
-        const int rows = ceil_div(g.TY, rb);
-        if (ceil_div(g.TY, rows) != rb) continue;
-        const long long units = (long long)p.tiles * rb;
-        const double waves = (double)((units + sms - 1) / sms);
-        const double cost = waves * (rows + 0.3 * (g.AY - 1) + 1.0);
-        if (best < 0 || cost < best * 0.999) { best = cost; p.rblocks = rb; p.rows_per_block = rows; }
-    }
-    p.units = (long long)p.tiles * p.rblocks;
-    p.grid = (int)(p.units < sms ? p.units : sms);
+    p.total = (long long)p.tiles * g.TY;
+    p.quota = (p.total + sms - 1) / sms;
+    const long long min_quota = g.TY < 8 ? g.TY : 8;
+    if (p.quota < min_quota) p.quota = min_quota;
+    p.grid = (int)((p.total + p.quota - 1) / p.quota);
+    p.units = (long long)p.grid * ((p.quota + g.TY - 2) / g.TY + 1);
     return true;
 }
 
@@ -113,11 +112,15 @@ struct Unit {
     int tile, ty0, ty1, r_lo, r_hi;
 };
 __device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan &p) {
+    // unit u = segment u / grid of CTA u % grid (gridDim.x == p.grid); empty (ty0 == ty1) past the CTA's last segment
     Unit w;
-    const int rb = (int)(u / p.tiles);
-    w.tile = (int)(u - (long long)rb * p.tiles);
-    w.ty0 = rb * p.rows_per_block;
-    w.ty1 = min(g.TY, w.ty0 + p.rows_per_block);
+    const long long b = u % p.grid, k = u / p.grid;
+    const long long lo = b * p.quota, hi = min(lo + p.quota, p.total);
+    w.tile = (int)(lo / g.TY + k);
+    const long long t0 = (long long)w.tile * g.TY;
+    const long long s0 = max(lo, t0), s1 = min(hi, t0 + g.TY);
+    w.ty0 = s1 > s0 ? (int)(s0 - t0) : 0;
+    w.ty1 = s1 > s0 ? (int)(s1 - t0) : 0;
     w.r_lo = max(0, w.ty0 - g.offy);
     w.r_hi = min(g.DY - 1, w.ty1 - 1 - g.offy + g.AY - 1);
     return w;
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
 #endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.ty0 >= w.ty1) break;                            // past this CTA's last segment
             // source element of every raw slot (q = t128 + 128 e -> channel q / RW, position q % RW) in row 0, or -1: zero
             long long roff[kRawMax];
 #pragma unroll
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
 #endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.ty0 >= w.ty1) break;                            // past this CTA's last segment
             const long long J = (long long)w.tile * kTile + i;
             const int n = (int)(J / p.TXP);
             const int tx = (int)(J - (long long)n * p.TXP);
@@ -396,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
 #endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.ty0 >= w.ty1) break;                            // past this CTA's last segment
             int next_new = w.ty0, next_done = w.ty0, win0 = w.ty0;
             slot_a = slot_new;
             for (int r = w.r_lo; r <= w.r_hi; ++r, ++stage) {

@@ -54,8 +54,8 @@ struct Plan {
     int VW, S;                      // virtual columns per sample, new output columns per tile
     int RS, NBUF, p_col0;           // ring slots, P buffers, first TMEM column of the P buffers
     int b_floats;                   // floats of ONE of the hi / lo halves of the atom operand
-    int tiles, rblocks, rows_per_block;
-    long long units;
+    int tiles;
+    long long total, quota, units;  // tile-rows of the problem, tile-rows per CTA, grid * (most segments of a CTA)
     int grid;
     size_t smem;
 };
@@ -94,18 +94,17 @@ bool make_plan(const Geo2 &g, Plan &p) {
     const long long cols = (long long)g.N * p.VW;
     if (cols <= 0 || cols >= (1ll << 31) - kTile) return false;
     p.tiles = (int)((cols + p.S - 1) / p.S);
+    // Work split: the (tile, row) space is cut into `grid` equal LINEAR ranges, one per CTA (a range is a few row segments
+    // of consecutive tiles) - every SM gets the same number of rows whatever the number of tiles (cfg2: 138 / 145 / 276
+    // tiles on 148 SMs left 7 - 10 % of the SMs idle with whole-tile units).  A segment boundary costs AY - 1 extra source
+    // rows, and there are at most two per CTA.
     const int sms = tma::sm_count();
-    double best = -1;
-    for (int rb = 1; rb <= g.DY && rb <= 64; ++rb) {
-        const int rows = ceil_div(g.DY, rb);
-        if (ceil_div(g.DY, rows) != rb) continue;
-        const long long units = (long long)p.tiles * rb;
-        const double waves = (double)((units + sms - 1) / sms);
-        const double cost = waves * (rows + 0.25 * (g.AY - 1) + 1.0);      // a row block stages AY-1 extra source rows
-        if (best < 0 || cost < best * 0.999) { best = cost; p.rblocks = rb; p.rows_per_block = rows; }
-    }
-    p.units = (long long)p.tiles * p.rblocks;
-    p.grid = (int)(p.units < sms ? p.units : sms);
+    p.total = (long long)p.tiles * g.DY;
+    p.quota = (p.total + sms - 1) / sms;
+    const long long min_quota = g.DY < 8 ? g.DY : 8;
+    if (p.quota < min_quota) p.quota = min_quota;
+    p.grid = (int)((p.total + p.quota - 1) / p.quota);
+    p.units = (long long)p.grid * ((p.quota + g.DY - 2) / g.DY + 1);
     return true;
 }
 
@@ -113,11 +112,15 @@ struct Unit {
     int tile, y0, y1, ta, tb;       // output rows [y0, y1), real source rows [ta, tb] (rows outside [0, TY) are zero: skipped)
 };
 __device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan &p) {
+    // unit u = segment u / grid of CTA u % grid (gridDim.x == p.grid); empty (y0 == y1) past the CTA's last segment
     Unit w;
-    const int rb = (int)(u / p.tiles);
-    w.tile = (int)(u - (long long)rb * p.tiles);
-    w.y0 = rb * p.rows_per_block;
-    w.y1 = min(g.DY, w.y0 + p.rows_per_block);
+    const long long b = u % p.grid, k = u / p.grid;
+    const long long lo = b * p.quota, hi = min(lo + p.quota, p.total);
+    w.tile = (int)(lo / g.DY + k);
+    const long long t0 = (long long)w.tile * g.DY;
+    const long long s0 = max(lo, t0), s1 = min(hi, t0 + g.DY);
+    w.y0 = s1 > s0 ? (int)(s0 - t0) : 0;
+    w.y1 = s1 > s0 ? (int)(s1 - t0) : 0;
     w.ta = max(w.y0 + g.offy - (g.AY - 1), 0);
     w.tb = min(w.y1 - 1 + g.offy, g.TY - 1);
     return w;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) recon_ts_kernel(const Geo2 g, con
 #endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.y0 >= w.y1) break;                            // past this CTA's last segment
             const long long F = (long long)w.tile * p.S + i;
             const int n = (int)(F / p.VW);
             const int v = (int)(F - (long long)n * p.VW) + g.offx - (AX - 1);
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) recon_ts_kernel(const Geo2 g, con
 #endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.y0 >= w.y1) break;                            // past this CTA's last segment
             const long long F0 = (long long)w.tile * p.S + i;
             const int n = (int)(F0 / p.VW);
             const int xo = (int)(F0 - (long long)n * p.VW);
@@ -389,6 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) recon_ts_kernel(const Geo2 g, con
 #endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
+            if (w.y0 >= w.y1) break;                            // past this CTA's last segment
             int next_new = w.ta, first = w.ta, next_rel = w.ta;
             slot_first = slot_new;
             slot_rel = slot_new;
