@@ -42,7 +42,10 @@ using tiled::round_up;
 constexpr int kCT = 64;             // activation columns per tile
 constexpr int kNB = 16;             // atoms per launch
 constexpr int kWorkers = 256;
-constexpr int kIssuers = 2;         // two issuing warps, each owning a FIXED half of the atom rows (= accumulator columns)
+#ifndef TNMF_GW_ISSUERS
+#define TNMF_GW_ISSUERS 2
+#endif
+constexpr int kIssuers = TNMF_GW_ISSUERS;   // issuing warps, each owning a FIXED share of the atom rows (= accumulator columns)
 constexpr int kThreads = 32 * (8 + kIssuers + 4);
 constexpr int kEpoch = 8;           // source rows accumulated into one TMEM set before it is drained
 constexpr int kMaxAStages = 4;
@@ -75,7 +78,11 @@ bool make_plan(const Geo2 &g, Plan &p) {
     if (p.KPL > 64) return false;
     p.NA = kNB * g.AY;
     const int spare = 512 - 2 * p.NA;
+#ifdef TNMF_GW_KS16
+    if (spare >= 2 * 32) p.KS = 16;
+#else
     if (spare >= 2 * 64) p.KS = 32;
+#endif
     else if (spare >= 2 * 32) p.KS = 16;
     else return false;
     p.n_sub = kCT / p.KS;
@@ -397,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
         // mirrored ring never splits a window; a split that moved with the ring's wrap-around made columns change hands
         // between rows and the accumulation order timing dependent (one-ulp run-to-run differences).
         const int X = warp - 8;
-        const int j_lo = X ? (AY + 1) / 2 : 0, j_hi = X ? AY - 1 : (AY + 1) / 2 - 1;
+        const int j_lo = (AY * X + kIssuers - 1) / kIssuers, j_hi = (AY * (X + 1) + kIssuers - 1) / kIssuers - 1;
         int st = 0;
         unsigned ph = 0;
         int rows_done = 0;
