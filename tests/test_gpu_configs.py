@@ -162,3 +162,59 @@ def test_two_ranks_unseeded_start_from_one_dictionary():
     assert np.array_equal(results[0][0], results[1][0])
     e = results[0][2]
     assert np.allclose(e, results[1][2], rtol=1e-12) and all(b <= a * (1 + 1e-6) for a, b in zip(e, e[1:]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# spatial (halo) sharding with the real kernels: bands of activation rows on two ranks
+# ---------------------------------------------------------------------------------------------------------
+def _halo_rank_main(rank, world, port, V, atoms, atom_shape, kw_fit, out):
+    import torch.distributed as dist
+    from tnmf_b200 import RowShardedNMF
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        np.random.seed(41)
+        nmf = RowShardedNMF(atoms, atom_shape)
+        energies = []
+        nmf.fit(V, progress_callback=lambda m, i: energies.append(m.energy()) or True, **kw_fit)
+        H = nmf.gather_H()
+        out[rank] = (nmf.W, H, energies, nmf.ops.be.kernel_names())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('case', ['f64', 'f32_tc'])
+def test_row_sharded_fit_equals_single_gpu_and_oracle(case):
+    """tnmf_b200.RowShardedNMF on two ranks (bands of activation rows, halo exchange every half iteration, W gradient of
+    the owned rows only, summed over the ranks) == the single-process oracle, with the CUDA kernels doing the arithmetic:
+    float64 on the generic kernels to 1e-9, float32 with 16 atoms of 3 x 11 x 11 on the tcgen05 kernels within the
+    north_star tolerances."""
+    import torch.multiprocessing as mp
+    rng = np.random.default_rng(8)
+    if case == 'f64':
+        V, atoms, atom_shape, iters = rng.random((3, 2, 24, 20)), 5, (5, 4), 10
+        rtol_e, tol = 1e-9, 1e-9
+    else:
+        V, atoms, atom_shape, iters = rng.random((2, 3, 96, 140), dtype=np.float32), 16, (11, 11), 20
+        rtol_e, tol = 1e-4, 1e-3
+    kw_fit = dict(n_iterations=iters, sparsity_H=0.05)
+    np.random.seed(41)
+    ref = orc.OracleNMF_FFT(n_atoms=atoms, atom_shape=atom_shape) if case != 'f64' else orc.OracleNMF(atoms, atom_shape)
+    e_ref = []
+    ref.fit_batch(V.astype(np.float64), progress_callback=lambda m, i: e_ref.append(float(m.energy())) or True, **kw_fit)
+    world = 2
+    ctx = mp.get_context('spawn')
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_halo_rank_main, args=(world, _free_port(), V, atoms, atom_shape, kw_fit, out), nprocs=world, join=True)
+        results = [out[r] for r in range(world)]
+    W0, H0, e0, names = results[0]
+    print(case, names, 'energy', e0[-1], e_ref[-1])
+    if case == 'f32_tc':
+        assert names == {'reconstruct': 'recon_ts_kernel', 'update_h': 'hupd_ts_kernel', 'gradient_w': 'gradw_ts_kernel'}
+    assert np.allclose(e0, e_ref, rtol=rtol_e)
+    assert np.abs(W0 - ref.W).max() <= tol * np.abs(ref.W).max()
+    assert np.abs(H0 - ref.H).max() <= tol * np.abs(ref.H).max()
+    assert np.array_equal(results[1][0], W0)

@@ -571,8 +571,10 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
                                                ws.data_ptr(), ws_bytes, st), 'update_h')
         self.launches += self._n_launches(p, _lib.OP_GRADIENT_H)
 
-    def gradient_W(self, V, W, H, s: slice, out: torch.Tensor) -> torch.Tensor:
-        """out[0] = neg, out[1] = pos of the W gradient on samples s (split-K + deterministic final reduction)."""
+    def gradient_W(self, V, W, H, s: slice, out: torch.Tensor, H_for_R: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """out[0] = neg, out[1] = pos of the W gradient on samples s (split-K + deterministic final reduction).
+        `H_for_R`: reconstruct from these activations instead of H (halo sharding correlates with a band of H - the other
+        rows zeroed - against the reconstruction of all of it; tnmf_b200/halo.py)."""
         Hs = H[s]
         Vs = self._device_V(V)[s]
         n = Hs.shape[0]
@@ -580,7 +582,9 @@ class B200_Backend(Backend):  # pylint: disable=invalid-name
         if n == 0:
             out.zero_()
             return out
-        R = self.reconstruct(W, Hs, out=self._R_for(n))
+        R = self.reconstruct(W, Hs if H_for_R is None else H_for_R[s], out=self._R_for(n))
+        if H_for_R is not None:
+            p, Hs = self._h_problem(Hs)         # (reconstruct recorded the other tensor's problem)
         ws, ws_bytes = self._workspace(p)
         with self._timed('gradient_w'):
             _lib.check(self._lib.tnmf_gradient_w(ctypes.byref(p), Vs.data_ptr(), R.data_ptr(), Hs.data_ptr(),
