@@ -495,6 +495,50 @@ def test_tc_gradient_w_vs_oracle(case, mode, tmem):
     _close(Wd, nmf.W, 5e-5)
 
 
+NS_CASES = [
+    # N, C, M, D, A: narrow atoms (C * A_x <= 16) - hi/lo, two source rows and both tensors stacked in the MMA lanes
+    (2, 1, 32, (40, 50), (15, 15)),     # cfg3 atoms: four launches of 8 atoms, window of 16 positions
+    (3, 1, 9, (31, 70), (4, 9)),        # even atom height (window padded 5 -> 8), odd number of source rows, 9 atoms = 8 + 1
+    (2, 2, 8, (25, 40), (7, 8)),        # two channels: all 16 tap lanes of a group in use
+    (40, 1, 4, (48, 500), (5, 5)),      # more work than one wave: several segments per CTA, many epochs
+    (1, 1, 5, (20, 24), (3, 3)),
+    (2, 2, 3, (6, 8), (6, 8)),          # atom as large as the sample
+    (2, 1, 20, (64, 64), (19, 16)),     # tallest atom it takes (window of 20), C * A_x = 16
+]
+
+
+@pytest.mark.parametrize('mode', ('valid', 'full'))
+@pytest.mark.parametrize('case', range(len(NS_CASES)))
+def test_tc_gradient_w_narrow_atoms_vs_oracle(case, mode):
+    """gradw_ns_kernel (BASELINE config 3's W gradient) against the oracle: both gradients, a minibatch slice, bitwise
+    repeatability, and the W update on top."""
+    N, C, M, D, A = NS_CASES[case]
+    rng = np.random.default_rng(800 + case)
+    V = rng.random((N, C) + D).astype(np.float32)
+    W = rng.random((M, C) + A).astype(np.float32)
+    H = rng.random((N, M) + orc.transform_shape(mode, D, A)).astype(np.float32)
+    V64, W64, H64 = V.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    be, Wd, Hd = _backend(V, W, H, mode, 'tc')
+    neg, pos = be.reconstruction_gradient_W(V, Wd, Hd)
+    assert be.kernel_names()['gradient_w'] == 'gradw_ns_kernel', be.kernel_names()
+    rn, rp = orc.reconstruction_gradient_W(V64, W64, H64, mode)
+    _close(neg, rn, 2e-5)
+    _close(pos, rp, 2e-5)
+    neg2, pos2 = be.reconstruction_gradient_W(V, Wd, Hd)
+    assert torch.equal(neg, neg2) and torch.equal(pos, pos2)
+    if N > 2:
+        neg, pos = be.reconstruction_gradient_W(V, Wd, Hd, slice(1, N - 1))
+        rn, rp = orc.reconstruction_gradient_W(V64[1:N - 1], W64, H64[1:N - 1], mode)
+        _close(neg, rn, 2e-5)
+        _close(pos, rp, 2e-5)
+    nmf = orc.OracleNMF(M, A, reconstruction_mode=mode)
+    nmf.V, nmf.W, nmf.H = V64, W64.copy(), H64.copy()
+    nmf.update_W()
+    grad = torch.empty((2, *Wd.shape), dtype=Wd.dtype, device=Wd.device)
+    be.apply_W_update(Wd, be.gradient_W(V, Wd, Hd, slice(None), grad))
+    _close(Wd, nmf.W, 5e-5)
+
+
 TALL_CASES = [
     # N, C, M, D, A  - atoms higher than the 15 rows one launch takes: the W gradient runs in atom-row chunks ('valid')
     (2, 1, 8, (40, 72), (20, 30)),      # two balanced chunks of 10 rows
@@ -531,10 +575,10 @@ def test_tc_gradient_w_tall_atoms_vs_oracle(case):
     a = torch.stack(be.reconstruction_gradient_W(V, Wd, Hd))
     b = torch.stack(be.reconstruction_gradient_W(V, Wd, Hd))
     assert torch.equal(a, b)
-    # 'full' mode has no chunked form: the FP32 kernels keep serving it
+    # 'full' mode has no chunked form: the FP32 kernels keep serving it (narrow atoms of up to 19 rows: gradw_ns does)
     be2, W2, H2 = _backend(V, W, rng.random((N, M) + orc.transform_shape('full', D, A)).astype(np.float32), 'full', 'tc')
     be2.reconstruct(W2, H2)
-    assert be2.kernel_families()['gradient_w'] != 'tc'
+    assert be2.kernel_families()['gradient_w'] != 'tc' or be2.kernel_names()['gradient_w'] == 'gradw_ns_kernel'
 
 
 @pytest.mark.parametrize('tmem', (True, False))        # expanded operand in tensor memory / in shared memory (round-1 kernels)

@@ -100,6 +100,25 @@ bool tmem_operand_gradw(const Geo &g, int dtype) {
     return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_gradw_ts_supported(g, dtype);
 }
 
+// The W gradient for narrow atoms (tc_gradw_ns.cu: C * A_x <= 16; hi / lo halves, two source rows and both tensors stacked
+// in the 128 MMA lanes, two MMAs per product): 'auto' takes it when at least half of the lanes carry taps.
+bool tmem_operand_gradw_ns(const Geo &g, int dtype) {
+    return !(g.flags & TNMF_FLAG_NO_TMEM_OPERAND) && tc_gradw_ns_supported(g, dtype);
+}
+bool tc_gradw_ns_worthwhile(const Geo &g) {
+    if (g.flags & TNMF_FLAG_NO_TC_GRADW) return false;
+    const int mp = (g.M + 7) / 8 * 8;
+    return 8 * g.C * g.A[2] >= 64 && (double)g.M / mp >= 0.5 && (long long)g.N * g.T[2] >= 64 && g.A[1] >= 3;
+}
+// which of the three tensor-core W gradients serves a problem whose family is TNMF_PATH_TC
+enum { GRADW_NS = 0, GRADW_TS = 1, GRADW_SS = 2 };
+int tc_gradw_variant(const tnmf_problem *p, const Geo &g) {
+    const bool forced = p->path == TNMF_PATH_TC;
+    if (tmem_operand_gradw_ns(g, p->dtype) && (forced || tc_gradw_ns_worthwhile(g))) return GRADW_NS;
+    if (tmem_operand_gradw(g, p->dtype)) return GRADW_TS;
+    return GRADW_SS;
+}
+
 // The reconstruction with the activation row ring in tensor memory: N = roundup(C * A_x, 16), K = atoms padded to 8, and
 // 128 - (A_x - 1) of the 128 MMA lanes produce outputs; 'auto' takes it when at least half of every MMA is useful work.
 bool tmem_operand_recon(const Geo &g, int dtype) {
@@ -150,6 +169,9 @@ int choose_family(const tnmf_problem *p, const Geo &g, int op, int *err) {
         return TNMF_PATH_TC;
     if (op == TNMF_OP_RECONSTRUCT && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_recon_worthwhile(g))) &&
         tc_recon_supported(g, p->dtype))
+        return TNMF_PATH_TC;
+    if (op == TNMF_OP_GRADIENT_W && tmem_operand_gradw_ns(g, p->dtype) &&
+        (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_gradw_ns_worthwhile(g))))
         return TNMF_PATH_TC;
     if (op == TNMF_OP_GRADIENT_W && (p->path == TNMF_PATH_TC || (p->path == TNMF_PATH_AUTO && tc_gradw_worthwhile(g))) &&
         (tc_gradw_supported(g, p->dtype) || tmem_operand_gradw(g, p->dtype)))
@@ -222,6 +244,10 @@ static size_t workspace_bytes_of(const Geo &g, int dtype) {
         const size_t w = align256(tc_gradw_ts_workspace_bytes(g));
         if (w > bytes) bytes = w;
     }
+    if (tc_gradw_ns_supported(g, dtype)) {
+        const size_t w = align256(tc_gradw_ns_workspace_bytes(g));
+        if (w > bytes) bytes = w;
+    }
     return bytes;
 }
 
@@ -266,7 +292,8 @@ const char *tnmf_kernel_name(const tnmf_problem *p, int op) {
         return v == RECON_TS ? "recon_ts_kernel" : v == RECON_OS ? "recon_os_kernel" : "recon_tc_kernel";
     }
     if (op == TNMF_OP_GRADIENT_H) return tmem_operand_hupd(g, p->dtype) ? "hupd_ts_kernel" : "hupd_tc_kernel";
-    return tmem_operand_gradw(g, p->dtype) ? "gradw_ts_kernel" : "gradw_tc_kernel";
+    const int v = tc_gradw_variant(p, g);
+    return v == GRADW_NS ? "gradw_ns_kernel" : v == GRADW_TS ? "gradw_ts_kernel" : "gradw_tc_kernel";
 }
 
 int tnmf_launch_count(const tnmf_problem *p, int op) {
@@ -277,7 +304,8 @@ int tnmf_launch_count(const tnmf_problem *p, int op) {
     const int f = choose_family(p, g, op, &err);
     if (f < 0) return -1;
     if (op == TNMF_OP_GRADIENT_W)                                                            // + the finishing reduction
-        return f != TNMF_PATH_TC ? 2 : tmem_operand_gradw(g, p->dtype) ? tc_gradw_ts_launches(g) : tc_gradw_launches(g);
+        return f != TNMF_PATH_TC ? 2 : tc_gradw_variant(p, g) == GRADW_NS ? tc_gradw_ns_launches(g)
+                                     : tc_gradw_variant(p, g) == GRADW_TS ? tc_gradw_ts_launches(g) : tc_gradw_launches(g);
     if (f == TNMF_PATH_TC) return op == TNMF_OP_RECONSTRUCT ? 1 : tc_hupd_launches(g);
     return f == TNMF_PATH_TMA ? 2 : 1;                                                      // + the atom pre-arrangement
 }
@@ -438,7 +466,11 @@ int tnmf_gradient_w(const tnmf_problem *p, const void *V, const void *R, const v
     if (s) return s;
     if (family == TNMF_PATH_TC) {
         if (!workspace || workspace_bytes < tnmf_workspace_bytes(p)) return TNMF_EWORKSPACE;
-        if (tmem_operand_gradw(g, p->dtype))
+        const int variant = tc_gradw_variant(p, g);
+        if (variant == GRADW_NS)
+            return tc_gradient_w_ns(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,
+                                    workspace, workspace_bytes, st);
+        if (variant == GRADW_TS)
             return tc_gradient_w_ts(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,
                                     workspace, workspace_bytes, st);
         return tc_gradient_w(g, (const float *)V, (const float *)R, (const float *)H, (float *)neg, (float *)pos,

@@ -106,6 +106,13 @@ int tc_gradw_ts_launches(const Geo &g);
 int tc_gradient_w_ts(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
                      size_t workspace_bytes, cudaStream_t st);
 
+// ---- implemented in tc_gradw_ns.cu (tcgen05 3xTF32, narrow atoms: hi/lo, two rows and both tensors stacked in the lanes) --
+bool tc_gradw_ns_supported(const Geo &g, int dtype);
+size_t tc_gradw_ns_workspace_bytes(const Geo &g);
+int tc_gradw_ns_launches(const Geo &g);
+int tc_gradient_w_ns(const Geo &g, const float *V, const float *R, const float *H, float *neg, float *pos, void *workspace,
+                     size_t workspace_bytes, cudaStream_t st);
+
 // ---- implemented in tc_recon.cu (tcgen05 3xTF32) ------------------------------------------------------------
 bool tc_recon_supported(const Geo &g, int dtype);
 int tc_recon_partials(const Geo &g);
