@@ -72,7 +72,10 @@ bool make_plan(const Geo2 &g, Plan &p) {
     if (p.KPL > 16) return false;
     p.WP = round_up(g.AY + 1, 4);
     p.NA = kNB * p.WP;
-    p.n_issue = p.WP % 8 == 0 ? 4 : 2;
+#ifndef TNMF_GWN_MAX_ISSUERS
+#define TNMF_GWN_MAX_ISSUERS 4
+#endif
+    p.n_issue = (p.WP % 8 == 0 && TNMF_GWN_MAX_ISSUERS >= 4) ? 4 : 2;
     p.n_astages = (512 - 2 * p.NA) / kKS;
     if (p.n_astages < 2) return false;
     if (p.n_astages > kMaxAStages) p.n_astages = kMaxAStages;
@@ -167,7 +170,8 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
         const int L = quarter * 32 + lane;                      // operand lane of this thread
         const int part = L >> 6, s_l = (L >> 5) & 1, X_l = (L >> 4) & 1, k = L & 15;
         const bool live = k < p.KPL;
-        const int src_off = live ? (s_l * 2 + X_l) * p.rawX + (k / AX) * p.RWp + (k % AX) : 4 * p.rawX + 16;
+        // idle lanes (k >= C * AX, so k = 15 is one of them) read zeros from bank 15 + col, which no live lane of the warp uses
+        const int src_off = live ? (s_l * 2 + X_l) * p.rawX + (k / AX) * p.RWp + (k % AX) : 4 * p.rawX + 15;
         const unsigned t_lane = tmem_base + ((unsigned)(quarter * 32) << 16) + (unsigned)(p.a_col0 + half * (kKS / 2));   // 32 columns
         int st = 0;
         unsigned a_wraps = 0, buf = 0;
@@ -176,6 +180,10 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
         const int h_sel = tid >> 7, h_ml = (tid >> 4) & 7, h_cg = tid & 15;     // activation chunk: row of the pair, atom,
         int slot_new = 0;                                                      // columns 4 cg .. 4 cg + 3
         unsigned wraps = 0;
+        TC_PROF_DECL(empty); TC_PROF_DECL(hfree); TC_PROF_DECL(bar); TC_PROF_DECL(total); TC_PROF_DECL(stw);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             if (w.ty0 >= w.ty1) break;                          // past this CTA's last segment
@@ -210,8 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
                 hoff[e] = (n < g.N && xv < g.TX && a.m0 + h_ml < g.M)
                               ? (long long)n * g.hsn + (long long)(a.m0 + h_ml) * g.hsm + xv : -1;
             }
-            float rv[kRawMax];
-            auto load_raw = [&](int r) {
+            auto load_raw = [&](int r, float (&rv)[kRawMax]) {
 #pragma unroll
                 for (int e = 0; e < kRawMax; ++e) {
                     const int row = r + (rsx[e] >> 1);
@@ -230,8 +237,8 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
                 }
                 return hv;
             };
-            auto stage_pair = [&](int t_pair, const float4 &hv) {   // rows t_pair, t_pair + 1 -> slots slot_new, slot_new + 1
-                if (wraps) mbar_wait_backoff(&h_free[slot_new >> 1], (wraps - 1u) & 1u, 40);
+            auto stage_pair = [&](const float4 &hv) {               // this thread's row of the next pair -> slots slot_new, slot_new + 1
+                if (wraps) TC_PROF_WAIT(hfree, mbar_wait_backoff(&h_free[slot_new >> 1], (wraps - 1u) & 1u, 40));
                 const int slot = slot_new + h_sel;
                 float4 hi, lo;
                 split_tf32(hv.x, hi.x, lo.x); split_tf32(hv.y, hi.y, lo.y);
@@ -248,56 +255,75 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
                 mbar_arrive(&h_full[slot_new >> 1]);
                 slot_new += 2;
                 if (slot_new == RS) { slot_new = 0; ++wraps; }
-                (void)t_pair;
             };
-            int t_next = w.j00;                                 // next pair of activation rows to stage
-            load_raw(w.r_lo);
-            float4 hv_next = load_h(t_next + h_sel);
-            for (int q = 0; q < w.steps; ++q) {
+            // One step.  Its raw rows and its (last) pair of activation rows were fetched TWO steps ago into (rv, hv): a step
+            // lasts ~1000 clk, a DRAM round trip about as long, so a distance of one step left the workers waiting for
+            // memory every step.  Once consumed the registers take the loads of step q + 2.
+            auto do_step = [&](int q, float (&rv)[kRawMax], float4 &hv) {
                 const int r = w.r_lo + 2 * q;
-                // ---- activation rows of this step's window that are not in the ring yet (WP at step 0, then 2) ----
-                const int t_end = w.j00 + 2 * q + WP;
-                while (t_next < t_end) {
-                    const float4 hv = hv_next;
-                    const int t_pair = t_next;
-                    t_next += 2;
-                    if (t_next < t_end) hv_next = load_h(t_next + h_sel);
-                    stage_pair(t_pair, hv);
+                if (q == 0) {                                       // the whole first window: WP / 2 pairs, the first one prefetched
+                    stage_pair(hv);
+                    for (int t = w.j00 + 2; t < w.j00 + WP; t += 2) stage_pair(load_h(t + h_sel));
+                } else {
+                    stage_pair(hv);                                 // rows j00 + WP + 2 (q - 1), + 1
                 }
-                // ---- raw V and R rows r, r + 1 of this tile (plain FP32; split when they are expanded) ----
                 float *rb = raw + (size_t)buf * p.raw_floats;
 #pragma unroll
                 for (int e = 0; e < kRawMax; ++e)
                     if (rdst[e] >= 0) rb[rdst[e]] = rv[e];
-                if (q + 1 < w.steps) {
-                    load_raw(r + 2);                                // in flight while this step is expanded
-                    hv_next = load_h(t_next + h_sel);
+                if (q + 2 < w.steps) {
+                    load_raw(r + 4, rv);
+                    hv = load_h(w.j00 + WP + 2 * (q + 1) + h_sel);
                 }
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                TC_PROF_WAIT(bar, asm volatile("bar.sync 1, 256;\n" ::: "memory"));
                 // ---- expansion into tensor memory: lane (part, s, X, c, ax) <- hi or lo of raw[s][X][c][ax + col] ----
                 const float *src = rb + src_off + half * (kKS / 2);
-                if (a_wraps) mbar_wait_backoff(&a_empty[st], (a_wraps - 1u) & 1u, 20);
+                if (a_wraps) TC_PROF_WAIT(empty, mbar_wait_backoff(&a_empty[st], (a_wraps - 1u) & 1u, 20));
                 tc_fence_after();
+                // hi = the nearest TF32 (add half an ulp of the 10-bit mantissa to the magnitude, clear the low 13 bits: what
+                // cvt.rna.tf32 does, without its inf/nan guard - two integer instructions), lo = x - hi (exact).  `part` is
+                // uniform in a warp: hi warps never compute lo.
 #pragma unroll
                 for (int h = 0; h < kKS / 32; ++h) {
                     float v[16];
+                    if (part == 0) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float hi, lo;
-                        split_tf32(src[h * 16 + j], hi, lo);
-                        v[j] = part ? lo : hi;
+                        for (int j = 0; j < 16; ++j)
+                            v[j] = __uint_as_float((__float_as_uint(src[h * 16 + j]) + 0x1000u) & 0xffffe000u);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float x = src[h * 16 + j];
+                            v[j] = x - __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+                        }
                     }
                     tmem_st16(t_lane + (unsigned)(st * kKS + h * 16), v);
                 }
-                tmem_st_wait();
+                TC_PROF_WAIT(stw, tmem_st_wait());
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[st]);
                 if (++st == p.n_astages) { st = 0; ++a_wraps; }
                 buf ^= 1u;
+            };
+            float rva[kRawMax], rvb[kRawMax];
+            float4 hva = load_h(w.j00 + h_sel), hvb = make_float4(0.f, 0.f, 0.f, 0.f);
+            load_raw(w.r_lo, rva);
+            if (w.steps > 1) {
+                load_raw(w.r_lo + 2, rvb);
+                hvb = load_h(w.j00 + WP + h_sel);
+            }
+            for (int q = 0; q < w.steps; q += 2) {
+                do_step(q, rva, hva);
+                if (q + 1 < w.steps) do_step(q + 1, rvb, hvb);
             }
             (void)r_hi;
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && tid == 0)
+            printf("gradw_ns workers: total %lld  wait a_empty %lld  wait h_free %lld  raw barrier %lld  tmem st wait %lld\n", prof_total, prof_empty, prof_hfree, prof_bar, prof_stw);
+#endif
     } else if (warp >= 8 + kIssuers) {
         // ------------------------------------ accumulator drainers ------------------------------------
         long long steps_total = 0;
@@ -314,10 +340,14 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
         float *slice = a.partials + ((long long)blockIdx.x * 4 + part * 2 + s_l) * 2 * count + (long long)X_l * count;
         const long long mstride = (long long)C * AY * AX;
         float *dst_base = slice + (((long long)a.m0 * C + c) * AY) * AX + ax;
+        TC_PROF_DECL(done); TC_PROF_DECL(total);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (int e = 0; e < n_epochs; ++e) {
             const int set = e & 1;
             const unsigned tbase = tmem_base + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(set * p.NA);
-            mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100);
+            TC_PROF_WAIT(done, mbar_wait_backoff(&set_done[set], (unsigned)((e >> 1) & 1), 100));
             tc_fence_after();
             for (int j = 0; j < WP; ++j) {
                 const int ay = AY - 1 - j + s_l;
@@ -342,6 +372,11 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
             tc_fence_before();
             mbar_arrive(&set_free[set]);
         }
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && tid == 32 * (8 + kIssuers))
+            printf("gradw_ns drainers: total %lld  wait set_done %lld  (%d epochs)\n", prof_total, prof_done, n_epochs);
+#endif
     } else {
         // ------------------------------------ MMA issuers (converged warps, one elected lane) ------------------------------------
         const unsigned tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -360,6 +395,10 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
         long long steps_done = 0;
         int slot_in = 0, slot_a = 0, slot_out = 0;              // next slot to be filled / first slot of the window / next to free
         unsigned par_in = 0;
+        TC_PROF_DECL(full); TC_PROF_DECL(hfull); TC_PROF_DECL(setfree); TC_PROF_DECL(total); TC_PROF_DECL(issue);
+#ifdef TNMF_TC_PROFILE
+        prof_total = -clock64();
+#endif
         for (long long u = blockIdx.x; X < p.n_issue && u < p.units; u += gridDim.x) {
             const Unit w = make_unit(u, g, p);
             if (w.ty0 >= w.ty1) break;
@@ -367,19 +406,22 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
             for (int q = 0; q < w.steps; ++q) {
                 const long long epoch = steps_done / kEpochSteps;
                 if (steps_done % kEpochSteps == 0 && epoch >= 2) {
-                    mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1));
+                    TC_PROF_WAIT(setfree, mbar_wait(&set_free[epoch & 1], (unsigned)(((epoch >> 1) - 1) & 1)));
                     tc_fence_after();
                 }
                 const unsigned tset = tmem_u + (unsigned)((epoch & 1) * p.NA) + (unsigned)(X * half_w * kNB);
                 // rows that enter the ring with this step: WP at the unit's first step, two afterwards
                 for (int i = q ? 2 : WP; i > 0; i -= 2) {
-                    mbar_wait(&h_full[slot_in >> 1], par_in);
+                    TC_PROF_WAIT(hfull, mbar_wait(&h_full[slot_in >> 1], par_in));
                     slot_in += 2;
                     if (slot_in == RS) { slot_in = 0; par_in ^= 1u; }
                 }
                 const unsigned b0 = (unsigned)(slot_a + X * half_w) * 8u;       // 8 ring rows = 128 bytes per slot
-                mbar_wait(&a_full[st], ph);
+                TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
                 tc_fence_after();
+#ifdef TNMF_TC_PROFILE
+                const long long t_i = clock64();
+#endif
                 const unsigned ta = tmem_u + (unsigned)(p.a_col0 + st * kKS);
                 if (elect_one()) {
 #pragma unroll
@@ -390,6 +432,9 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
                     }
                 }
                 __syncwarp();
+#ifdef TNMF_TC_PROFILE
+                prof_issue += clock64() - t_i;
+#endif
                 mma_commit_elect(&a_empty[st]);
                 if (++st == p.n_astages) { st = 0; ph ^= 1u; }
                 // activation rows that leave the window: two per step, the whole window after the unit's last step
@@ -404,6 +449,11 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
             }
         }
         if (X < p.n_issue && steps_done % kEpochSteps != 0) mma_commit_elect(&set_done[(steps_done / kEpochSteps) & 1]);
+#ifdef TNMF_TC_PROFILE
+        prof_total += clock64();
+        if (blockIdx.x == 0 && lane == 0 && X < p.n_issue)
+            printf("gradw_ns mma %d: total %lld  wait a_full %lld  wait h_full %lld  wait set_free %lld  issuing %lld (%lld steps)\n", X, prof_total, prof_full, prof_hfull, prof_setfree, prof_issue, steps_done);
+#endif
         __syncwarp();
     }
     tc_fence_before();
