@@ -73,7 +73,7 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.WP = round_up(g.AY + 1, 4);
     p.NA = kNB * p.WP;
 #ifndef TNMF_GWN_MAX_ISSUERS
-#define TNMF_GWN_MAX_ISSUERS 4
+#define TNMF_GWN_MAX_ISSUERS 2
 #endif
     p.n_issue = (p.WP % 8 == 0 && TNMF_GWN_MAX_ISSUERS >= 4) ? 4 : 2;
     p.n_astages = (512 - 2 * p.NA) / kKS;
@@ -412,12 +412,12 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ns_kernel(const Geo2 g, con
                 const unsigned tset = tmem_u + (unsigned)((epoch & 1) * p.NA) + (unsigned)(X * half_w * kNB);
                 // rows that enter the ring with this step: WP at the unit's first step, two afterwards
                 for (int i = q ? 2 : WP; i > 0; i -= 2) {
-                    TC_PROF_WAIT(hfull, mbar_wait(&h_full[slot_in >> 1], par_in));
+                    TC_PROF_WAIT(hfull, mbar_wait_backoff(&h_full[slot_in >> 1], par_in, 20));
                     slot_in += 2;
                     if (slot_in == RS) { slot_in = 0; par_in ^= 1u; }
                 }
                 const unsigned b0 = (unsigned)(slot_a + X * half_w) * 8u;       // 8 ring rows = 128 bytes per slot
-                TC_PROF_WAIT(full, mbar_wait(&a_full[st], ph));
+                TC_PROF_WAIT(full, mbar_wait_backoff(&a_full[st], ph, 20));
                 tc_fence_after();
 #ifdef TNMF_TC_PROFILE
                 const long long t_i = clock64();
