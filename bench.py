@@ -279,7 +279,7 @@ def time_steps(nmf_cls, w, n_local, device, args, steps, warmup, sharded, dist):
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
     if sharded:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    families = nmf._backend.kernel_families()                            # pylint: disable=protected-access
+    families = dict(nmf._backend.kernel_families(), kernels=nmf._backend.kernel_names())   # pylint: disable=protected-access
     finite = bool(torch.isfinite(nmf.energy_device()).item())
     del nmf, V, step
     torch.cuda.empty_cache()
@@ -510,7 +510,7 @@ def run_b200(args, w):
                    'parallelism': (f'sample-sharded x{world}, W gradient summed over the ranks '
                                    + ('inside the W-update kernel over NVLink peer memory' if peer_active
                                       else 'by an NCCL all-reduce')) if world > 1 else 'single GPU',
-                   'kernel_path': be.kernel_families(), 'launch': 'CUDA graph replay of one iteration' if nmf._cuda_graph  # pylint: disable=protected-access
+                   'kernel_path': be.kernel_families(), 'kernels': be.kernel_names(), 'launch': 'CUDA graph replay of one iteration' if nmf._cuda_graph  # pylint: disable=protected-access
                    else 'eager launches',
                    'l2': 'working set (V, R, H) exceeds the 126 MB L2; no explicit flush'
                    if (bytes_step / 5 > 126e6) else 'working set fits L2; iterations overwrite H and R in between',
