@@ -61,6 +61,7 @@ struct Plan {
                                     // AY - 1 slots are mirrored behind the last one), floats of ONE of the hi / lo halves
     int tiles;
     long long total, quota, units;  // tile-rows of the problem, tile-rows per CTA, grid * (most segments of a CTA)
+    int round_robin;                // 1: unit u is the whole tile u (CTA u % grid); 0: linear ranges
     int grid;
     size_t smem;
 };
@@ -119,11 +120,18 @@ bool make_plan(const Geo2 &g, Plan &p) {
     p.quota = (p.total + sms - 1) / sms;
     const long long min_quota = g.TY < 8 ? g.TY : 8;
     if (p.quota < min_quota) p.quota = min_quota;
-    // Whole tiles per CTA when that costs little: CTAs then walk down the same rows at the same time and share the V / R
-    // rows of a sample in L2 (ncu, cfg2: 394 MB of DRAM reads with whole tiles, 601 MB with ranges that start anywhere, for
-    // 1.4 % of kernel time)
+    // Whole tiles, dealt ROUND-ROBIN, when that costs little: the CTAs then work on consecutive tiles and walk down the same
+    // rows at the same time, so the tiles of a sample share its V / R rows (and the activation sectors at tile borders) in
+    // L2.  ncu, cfg2: 394 MB of DRAM reads per launch this way against 580 - 600 MB when every CTA owns a contiguous range
+    // of the (tile, row) space, for 1.4 % of kernel time.
     const long long whole = (p.tiles + sms - 1) / sms * (long long)g.TY;
-    if ((double)whole <= 1.1 * (double)(p.quota + 2 * (g.AY - 1))) p.quota = whole;
+    p.round_robin = (double)whole <= 1.1 * (double)(p.quota + 2 * (g.AY - 1));
+    if (p.round_robin) {
+        p.quota = g.TY;
+        p.grid = p.tiles < sms ? p.tiles : sms;
+        p.units = p.tiles;
+        return true;
+    }
     p.grid = (int)((p.total + p.quota - 1) / p.quota);
     p.units = (long long)p.grid * ((p.quota + g.TY - 2) / g.TY + 1);
     return true;
@@ -136,8 +144,8 @@ __device__ __forceinline__ Unit make_unit(long long u, const Geo2 &g, const Plan
     // unit u = segment u / grid of CTA u % grid (gridDim.x == p.grid); empty (ty0 == ty1) past the CTA's last segment
     Unit w;
     const long long b = u % p.grid, k = u / p.grid;
-    const long long lo = b * p.quota, hi = min(lo + p.quota, p.total);
-    w.tile = (int)(lo / g.TY + k);
+    const long long lo = p.round_robin ? u * (long long)g.TY : b * p.quota, hi = min(lo + p.quota, p.total);
+    w.tile = p.round_robin ? (int)u : (int)(lo / g.TY + k);
     const long long t0 = (long long)w.tile * g.TY;
     const long long s0 = max(lo, t0), s1 = min(hi, t0 + g.TY);
     w.ty0 = s1 > s0 ? (int)(s0 - t0) : 0;
