@@ -427,27 +427,47 @@ __global__ void __launch_bounds__(kThreads, 1) recon_ts_kernel(const Geo2 g, con
 #endif
                     const unsigned tp = tmem_u + (unsigned)(p.p_col0 + my_buf * NP);
                     if (elect_one()) {
+                        // The issuing lane must hand the pipe an MMA every N/2 = 24 clk: nothing but uniform adds may stand
+                        // between two of them.  The K steps are a compile-time count (KM = 2 * APT), the one non-accumulating
+                        // MMA of the row is peeled off (a `fresh` flag inside the loop cost a vote and six moves per K step -
+                        // ncu: tensor pipe 62 % active with the issuing warps never waiting), and the row is cut at its
+                        // middle for the hand-over to the other warp instead of testing for it in every iteration.
+                        constexpr int kSteps = APT / 4;
                         int s = slot_first;
                         unsigned bo = (unsigned)(y + g.offy - t_first) * b_ay16;    // matrix of ay = y + offy - ty
-                        bool fresh = true;
-                        const int t_mid = (t_first + t_last + 1) >> 1;
-                        for (int ty = t_first; ty <= t_last; ++ty) {
+                        {
                             const unsigned ta_hi = tmem_u + (unsigned)(s * KM), ta_lo = ta_hi + lo_off;
-                            if (ty == t_mid) mbar_arrive(&turn[x ^ 1]);             // the other warp may start on the next row
+                            mma_tf32_ts2<false>(tp, ta_hi, w_hi + bo, desc_hi, idesc);
+                            mma_tf32_ts2<true>(tp, ta_lo, w_hi + bo, desc_hi, idesc);
+                            mma_tf32_ts2<true>(tp, ta_hi, w_lo + bo, desc_hi, idesc);
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                if (ks < ksteps) {
-                                    const unsigned kb = bo + (unsigned)ks * b_step16;
-                                    if (fresh) mma_tf32_ts2<false>(tp, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc);
-                                    else mma_tf32_ts2<true>(tp, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc);
-                                    fresh = false;
-                                    mma_tf32_ts2<true>(tp, ta_lo + 8u * ks, w_hi + kb, desc_hi, idesc);
-                                    mma_tf32_ts2<true>(tp, ta_hi + 8u * ks, w_lo + kb, desc_hi, idesc);
-                                }
+                            for (int ks = 1; ks < kSteps; ++ks) {
+                                const unsigned kb = bo + (unsigned)ks * b_step16;
+                                mma_tf32_ts2<true>(tp, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc);
+                                mma_tf32_ts2<true>(tp, ta_lo + 8u * ks, w_hi + kb, desc_hi, idesc);
+                                mma_tf32_ts2<true>(tp, ta_hi + 8u * ks, w_lo + kb, desc_hi, idesc);
                             }
                             if (++s == RS) s = 0;
                             bo -= b_ay16;
                         }
+                        const int t_mid = max((t_first + t_last + 1) >> 1, t_first + 1);
+                        auto rows = [&](int ty_a, int ty_b) {
+                            for (int ty = ty_a; ty < ty_b; ++ty) {
+                                const unsigned ta_hi = tmem_u + (unsigned)(s * KM), ta_lo = ta_hi + lo_off;
+#pragma unroll
+                                for (int ks = 0; ks < kSteps; ++ks) {
+                                    const unsigned kb = bo + (unsigned)ks * b_step16;
+                                    mma_tf32_ts2<true>(tp, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc);
+                                    mma_tf32_ts2<true>(tp, ta_lo + 8u * ks, w_hi + kb, desc_hi, idesc);
+                                    mma_tf32_ts2<true>(tp, ta_hi + 8u * ks, w_lo + kb, desc_hi, idesc);
+                                }
+                                if (++s == RS) s = 0;
+                                bo -= b_ay16;
+                            }
+                        };
+                        rows(t_first + 1, min(t_mid, t_last + 1));
+                        mbar_arrive(&turn[x ^ 1]);                                  // the other warp may start on the next row
+                        rows(t_mid, t_last + 1);
                     }
                     __syncwarp();
 #ifdef TNMF_TC_PROFILE
