@@ -343,8 +343,8 @@ __global__ void __launch_bounds__(kThreads, 1) recon_os_kernel(const Geo2 g, con
         const unsigned w_hi = __shfl_sync(0xffffffffu, (smem_u32(b_hi) >> 4) + ((unsigned)NB << 16), 0);
         const unsigned w_lo = __shfl_sync(0xffffffffu, (smem_u32(b_lo) >> 4) + ((unsigned)NB << 16), 0);
         const unsigned b_step16 = 2u * (unsigned)NB;
-        const int ksteps = p.ksteps;
-        int st = 0;
+        constexpr int kSteps = APT / 4;                         // K steps: KM = 2 * APT atoms, 8 per MMA (compile time: the
+        int st = 0;                                             // issue loop is uniform adds between MMAs, nothing else)
         unsigned ph = 0;
         int slot_in = 0, slot_lo = 0, slot_out = 0;            // slot of the next row to enter / of the window's first row /
         unsigned wraps_in = 0;                                  // of the next row to complete
@@ -378,19 +378,25 @@ __global__ void __launch_bounds__(kThreads, 1) recon_os_kernel(const Geo2 g, con
                 const unsigned idesc0 = idesc_tf32(kTile, first * NP), idesc1 = idesc_tf32(kTile, max(second, 1) * NP);
                 const unsigned ta_hi = tmem_u + (unsigned)(p.a_col0 + st * 2 * KM), ta_lo = ta_hi + (unsigned)KM;
                 if (elect_one()) {
+                    if (second > 0) {                           // the window wraps around the ring: two runs of slots
+                        const unsigned bo1 = bo + (unsigned)(first * NP);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        if (ks < ksteps) {
+                        for (int ks = 0; ks < kSteps; ++ks) {
+                            const unsigned kb = bo + (unsigned)ks * b_step16, kb1 = bo1 + (unsigned)ks * b_step16;
+                            mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(tmem_u, ta_hi + 8u * ks, w_hi + kb1, desc_hi, idesc1);
+                            mma_tf32_ts2<true>(d0, ta_lo + 8u * ks, w_hi + kb, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(tmem_u, ta_lo + 8u * ks, w_hi + kb1, desc_hi, idesc1);
+                            mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_lo + kb, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(tmem_u, ta_hi + 8u * ks, w_lo + kb1, desc_hi, idesc1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < kSteps; ++ks) {
                             const unsigned kb = bo + (unsigned)ks * b_step16;
                             mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc0);
                             mma_tf32_ts2<true>(d0, ta_lo + 8u * ks, w_hi + kb, desc_hi, idesc0);
                             mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_lo + kb, desc_hi, idesc0);
-                            if (second > 0) {                   // the window wraps around the ring
-                                const unsigned kb1 = kb + (unsigned)(first * NP);
-                                mma_tf32_ts2<true>(tmem_u, ta_hi + 8u * ks, w_hi + kb1, desc_hi, idesc1);
-                                mma_tf32_ts2<true>(tmem_u, ta_lo + 8u * ks, w_hi + kb1, desc_hi, idesc1);
-                                mma_tf32_ts2<true>(tmem_u, ta_hi + 8u * ks, w_lo + kb1, desc_hi, idesc1);
-                            }
                         }
                     }
                 }
