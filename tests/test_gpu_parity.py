@@ -645,7 +645,7 @@ def test_tc_reconstruct_narrow_atoms_vs_oracle(case, mode):
         assert be2.kernel_names()['reconstruct'] == 'recon_os_kernel', be2.kernel_names()
 
 
-@pytest.mark.parametrize('seed', range(10))
+@pytest.mark.parametrize('seed', range(16))
 def test_tc_kernels_vs_generic_on_random_shapes(seed):
     """Randomly drawn supported shapes (ragged tiles, rows far beyond one trip round the TMEM / activation rings, atom
     counts off the blocks of 16, both modes): the tensor-core kernels against the one-thread-per-output generic kernels

@@ -431,15 +431,30 @@ __global__ void __launch_bounds__(kThreads, 1) hupd_ts_kernel(const Geo2 g, cons
                 const unsigned b0 = (unsigned)(t_a - j0) * 16u, b1 = b0 + (unsigned)first * 16u;
                 const bool two = cnt > first;
                 if (elect_one()) {
-                    for (int ks = 0; ks < ksteps; ++ks) {
-                        const unsigned kb = (unsigned)ks * b_step16;
-                        if (2 * ks == ksteps - 1 || 2 * ks == ksteps) mbar_arrive(&turn[X ^ 1]);   // half way: the other warp may start
-                        mma_tf32_ts2<true>(col0, ta_hi + 8u * ks, w_hi_word + kb + b0, desc_hi, idesc0);
-                        if (two) mma_tf32_ts2<true>(ring0, ta_hi + 8u * ks, w_hi_word + kb + b1, desc_hi, idesc1);
-                        mma_tf32_ts2<true>(col0, ta_lo + 8u * ks, w_hi_word + kb + b0, desc_hi, idesc0);
-                        if (two) mma_tf32_ts2<true>(ring0, ta_lo + 8u * ks, w_hi_word + kb + b1, desc_hi, idesc1);
-                        mma_tf32_ts2<true>(col0, ta_hi + 8u * ks, w_lo_word + kb + b0, desc_hi, idesc0);
-                        if (two) mma_tf32_ts2<true>(ring0, ta_hi + 8u * ks, w_lo_word + kb + b1, desc_hi, idesc1);
+                    // compile-time K steps, the wrap branch outside the loop, the hand-over at a fixed step: between two MMAs
+                    // the issuing lane executes uniform adds only
+                    constexpr int kSteps = KPT / 8, kMid = (kSteps - 1) / 2;
+                    if (two) {
+#pragma unroll
+                        for (int ks = 0; ks < kSteps; ++ks) {
+                            const unsigned kb = (unsigned)ks * b_step16;
+                            if (ks == kMid) mbar_arrive(&turn[X ^ 1]);              // half way: the other warp may start
+                            mma_tf32_ts2<true>(col0, ta_hi + 8u * ks, w_hi_word + kb + b0, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(ring0, ta_hi + 8u * ks, w_hi_word + kb + b1, desc_hi, idesc1);
+                            mma_tf32_ts2<true>(col0, ta_lo + 8u * ks, w_hi_word + kb + b0, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(ring0, ta_lo + 8u * ks, w_hi_word + kb + b1, desc_hi, idesc1);
+                            mma_tf32_ts2<true>(col0, ta_hi + 8u * ks, w_lo_word + kb + b0, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(ring0, ta_hi + 8u * ks, w_lo_word + kb + b1, desc_hi, idesc1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < kSteps; ++ks) {
+                            const unsigned kb = (unsigned)ks * b_step16;
+                            if (ks == kMid) mbar_arrive(&turn[X ^ 1]);
+                            mma_tf32_ts2<true>(col0, ta_hi + 8u * ks, w_hi_word + kb + b0, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(col0, ta_lo + 8u * ks, w_hi_word + kb + b0, desc_hi, idesc0);
+                            mma_tf32_ts2<true>(col0, ta_hi + 8u * ks, w_lo_word + kb + b0, desc_hi, idesc0);
+                        }
                     }
                 }
                 __syncwarp();
