@@ -238,11 +238,13 @@ __device__ __forceinline__ void tmem_st16_zero(unsigned addr) {
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
-// x = hi + lo with hi the nearest TF32 (10-bit mantissa) and lo the remainder (the MMA truncates it to TF32).
+// x = hi + lo with hi the nearest TF32 (10-bit mantissa, ties away from zero) and lo the remainder (the MMA truncates it to
+// TF32).  hi is what cvt.rna.tf32.f32 returns for finite x - half an ulp of the short mantissa added to the magnitude, the
+// low 13 bits cleared - in two integer instructions: the cvt compiles to four (it guards inf / nan), and the expanding
+// warps of the tensor-core kernels, which split every operand element, are instruction-bound (ncu: gradw_ns 845 M warp
+// instructions per launch; gradw_ts workers busy 83 % of the kernel).  inf stays inf, nan stays nan.
 __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-    unsigned h;
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
 }
 

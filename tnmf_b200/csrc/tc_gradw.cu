@@ -38,8 +38,13 @@ namespace gw {
 #ifndef TNMF_GW_EPOCH
 #define TNMF_GW_EPOCH 8
 #endif
+// ONE issuing warp: with two, the window was cut where the ring wraps, so an accumulator column changed hands between
+// source rows and the tensor pipe does not execute the MMAs of different warps in issue order - the truncating
+// accumulation then depended on timing (tools/determinism_check.py: one-ulp run-to-run differences; tc_gradw_ts.cu avoids
+// it with a mirrored ring and a static split).  This kernel is the fallback form now: it pays ~7 % for being bitwise
+// reproducible.
 #ifndef TNMF_GW_ISSUERS
-#define TNMF_GW_ISSUERS 2
+#define TNMF_GW_ISSUERS 1
 #endif
 constexpr int kCT = 64;             // activation columns per tile = contraction length of one source row
 constexpr int kNB = 16;             // atoms per launch
@@ -416,25 +421,9 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                 // accumulate into disjoint TMEM columns in a fixed order - the result does not depend on how the two
                 // warps interleave in the tensor pipe (splitting the K steps between the warps did: bitwise
                 // run-to-run differences, caught by the graph-vs-eager test).
-                unsigned o_col = 0, o_idesc = 0, o_b16 = 0;
-                bool have = false;
-                {
-                    const int cnt = t_b - t_a + 1;
-                    const int s0 = (int)((g_base + (t_a - w.ty0)) % RS);
-                    int first = min(cnt, RS - s0);                      // slots before the wrap-around
-                    if (kIssuers > 1 && first == cnt && cnt > 1) first = (cnt + 1) / 2;
-                    if (kIssuers == 1 || x == 0) {
-                        have = true;
-                        o_col = (unsigned)((t_a - j0) * kNB); o_idesc = idesc_tf32(128, kNB * first); o_b16 = (unsigned)s0 * 16u;
-                    } else if (x == 1 && cnt > first) {
-                        have = true;
-                        o_col = (unsigned)((t_a - j0 + first) * kNB); o_idesc = idesc_tf32(128, kNB * (cnt - first));
-                        o_b16 = (unsigned)((s0 + first) % RS) * 16u;
-                    }
-                }
                 const unsigned a_hi16 = (stage_addr0 + (unsigned)st * 2u * (unsigned)p.stage_floats * 4u) >> 4;
                 const unsigned a_addr16[3] = {a_hi16, a_hi16 + (((unsigned)p.stage_floats * 4u) >> 4), a_hi16};
-                if (have) {
+                auto issue_run = [&](unsigned o_col, unsigned o_idesc, unsigned o_b16) {
                     for (int ks = 0; ks < kCT / 8; ++ks) {
 #pragma unroll
                         for (int t = 0; t < 3; ++t) {
@@ -445,6 +434,17 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_tc_kernel(const Geo2 g, con
                                            ((unsigned long long)desc_hi << 32) | (b_lo_word | (b16 + o_b16)), o_idesc, 1u);
                         }
                     }
+                };
+                {
+                    const int cnt = t_b - t_a + 1;
+                    const int s0 = (int)((g_base + (t_a - w.ty0)) % RS);
+                    int first = min(cnt, RS - s0);                      // slots before the wrap-around
+                    if (kIssuers > 1 && first == cnt && cnt > 1) first = (cnt + 1) / 2;
+                    if (kIssuers == 1 || x == 0)
+                        issue_run((unsigned)((t_a - j0) * kNB), idesc_tf32(128, kNB * first), (unsigned)s0 * 16u);
+                    if ((kIssuers == 1 || x == 1) && cnt > first)
+                        issue_run((unsigned)((t_a - j0 + first) * kNB), idesc_tf32(128, kNB * (cnt - first)),
+                                  (unsigned)((s0 + first) % RS) * 16u);
                 }
                 mma_commit_elect(&a_empty[st]);
                 if (++st == p.n_stages) { st = 0; ph ^= 1u; }

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
         // slot of the first row of the window
         int slot_new = 0, slot_out = 0, slot_a = 0;
         unsigned par_new = 0;
-        TC_PROF_DECL(full); TC_PROF_DECL(hfull); TC_PROF_DECL(setfree); TC_PROF_DECL(total); TC_PROF_DECL(issue);
+        TC_PROF_DECL(full); TC_PROF_DECL(hfull); TC_PROF_DECL(setfree); TC_PROF_DECL(total); TC_PROF_DECL(issue); TC_PROF_DECL(commit); TC_PROF_DECL(commit2);
 #ifdef TNMF_TC_PROFILE
         prof_total = -clock64();
 #endif
@@ -479,13 +479,13 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
 #ifdef TNMF_TC_PROFILE
                     prof_issue += clock64() - t_i;
 #endif
-                    mma_commit_elect(&a_empty[st]);
+                    TC_PROF_WAIT(commit, mma_commit_elect(&a_empty[st]));
                     if (++st == p.n_astages) { st = 0; ph ^= 1u; }
                 }
                 // activation rows that leave the window: their slots may be overwritten once these MMAs are done (both
                 // warps commit: h_free counts two arrivals, each commit covers the committing warp's own MMAs)
                 for (; next_out < w.ty1 && min(g.DY - 1, next_out - g.offy + AY - 1) <= r; ++next_out) {
-                    mma_commit_elect(&h_free[slot_out]);
+                    TC_PROF_WAIT(commit2, mma_commit_elect(&h_free[slot_out]));
                     if (++slot_out == RS) slot_out = 0;
                 }
                 if (++rows_done % kEpoch == 0) mma_commit_elect(&set_done[epoch & 1]);
@@ -495,8 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) gradw_ts_kernel(const Geo2 g, con
 #ifdef TNMF_TC_PROFILE
         prof_total += clock64();
         if (blockIdx.x == 0 && lane == 0)
-            printf("gradw_ts mma %d: total %lld  wait a_full %lld  wait h_full %lld  wait set_free %lld  issuing %lld (%d rows)\n",
-                   X, prof_total, prof_full, prof_hfull, prof_setfree, prof_issue, rows_done);
+            printf("gradw_ts mma %d: total %lld  wait a_full %lld  wait h_full %lld  wait set_free %lld  issuing %lld  commit a_empty %lld  commit h_free %lld (%d rows)\n",
+                   X, prof_total, prof_full, prof_hfull, prof_setfree, prof_issue, prof_commit, prof_commit2, rows_done);
 #endif
         __syncwarp();
     }
