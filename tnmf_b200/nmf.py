@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .backend import B200_Backend
-from .distributed import PeerExchange, SampleSharding, equal_batch_slices
+from .distributed import SampleSharding, equal_batch_slices
 
 sliceNone = slice(None)
 
