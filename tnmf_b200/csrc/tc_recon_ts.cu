@@ -450,7 +450,10 @@ __global__ void __launch_bounds__(kThreads, 1) recon_ts_kernel(const Geo2 g, con
                             if (++s == RS) s = 0;
                             bo -= b_ay16;
                         }
-                        const int t_mid = max((t_first + t_last + 1) >> 1, t_first + 1);
+#ifndef TNMF_RCT_TURN_DIV
+#define TNMF_RCT_TURN_DIV 2
+#endif
+                        const int t_mid = max(t_first + (t_last - t_first + 1) / TNMF_RCT_TURN_DIV, t_first + 1);
                         auto rows = [&](int ty_a, int ty_b) {
                             for (int ty = ty_a; ty < ty_b; ++ty) {
                                 const unsigned ta_hi = tmem_u + (unsigned)(s * KM), ta_lo = ta_hi + lo_off;
