@@ -352,67 +352,112 @@ __global__ void __launch_bounds__(kThreads, 1) recon_os_kernel(const Geo2 g, con
 #ifdef TNMF_TC_PROFILE
         prof_total = -clock64();
 #endif
-        for (long long u = blockIdx.x; u < p.units; u += gridDim.x) {
-            const Unit w = make_unit(u, g, p);
-            if (w.y0 >= w.y1) break;                            // past this CTA's last segment
-            int next_in = w.y0, win_lo = w.y0, next_out = w.y0;
-            slot_lo = slot_in;                                  // the unit's first output row enters here
-            for (int ty = w.ta; ty <= w.tb; ++ty) {
-                const int yhi = min(w.y1 - 1, ty - g.offy + AY - 1), ylo = max(w.y0, ty - g.offy);
-                // output rows that enter the window with this source row: their slots must have been drained
-                for (; next_in <= yhi; ++next_in) {
-                    if (wraps_in) TC_PROF_WAIT(dfree, mbar_wait(&d_free[slot_in], (wraps_in - 1u) & 1u));
-                    if (++slot_in == RSD) { slot_in = 0; ++wraps_in; }
-                }
-                for (; win_lo < ylo; ++win_lo)
-                    if (++slot_lo == RSD) slot_lo = 0;
-                TC_PROF_WAIT(afull, mbar_wait(&a_full[st], ph));
-                tc_fence_after();
-#ifdef TNMF_TC_PROFILE
-                const long long t_i = clock64();
-#endif
-                const int cnt = yhi - ylo + 1;                  // >= 1: every source row of a unit meets one of its output rows
-                const int first = min(cnt, RSD - slot_lo), second = cnt - first;
-                const unsigned bo = (unsigned)((ylo + g.offy - ty) * NP);       // first row block of B: ay of the window's first row
-                const unsigned d0 = tmem_u + (unsigned)(slot_lo * NP);
-                const unsigned idesc0 = idesc_tf32(kTile, first * NP), idesc1 = idesc_tf32(kTile, max(second, 1) * NP);
-                const unsigned ta_hi = tmem_u + (unsigned)(p.a_col0 + st * 2 * KM), ta_lo = ta_hi + (unsigned)KM;
-                if (elect_one()) {
-                    if (second > 0) {                           // the window wraps around the ring: two runs of slots
-                        const unsigned bo1 = bo + (unsigned)(first * NP);
-#pragma unroll
-                        for (int ks = 0; ks < kSteps; ++ks) {
-                            const unsigned kb = bo + (unsigned)ks * b_step16, kb1 = bo1 + (unsigned)ks * b_step16;
-                            mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc0);
-                            mma_tf32_ts2<true>(tmem_u, ta_hi + 8u * ks, w_hi + kb1, desc_hi, idesc1);
-                            mma_tf32_ts2<true>(d0, ta_lo + 8u * ks, w_hi + kb, desc_hi, idesc0);
-                            mma_tf32_ts2<true>(tmem_u, ta_lo + 8u * ks, w_hi + kb1, desc_hi, idesc1);
-                            mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_lo + kb, desc_hi, idesc0);
-                            mma_tf32_ts2<true>(tmem_u, ta_hi + 8u * ks, w_lo + kb1, desc_hi, idesc1);
-                        }
-                    } else {
-#pragma unroll
-                        for (int ks = 0; ks < kSteps; ++ks) {
-                            const unsigned kb = bo + (unsigned)ks * b_step16;
-                            mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_hi + kb, desc_hi, idesc0);
-                            mma_tf32_ts2<true>(d0, ta_lo + 8u * ks, w_hi + kb, desc_hi, idesc0);
-                            mma_tf32_ts2<true>(d0, ta_hi + 8u * ks, w_lo + kb, desc_hi, idesc0);
-                        }
-                    }
-                }
-                __syncwarp();
-#ifdef TNMF_TC_PROFILE
-                prof_issue += clock64() - t_i;
-#endif
-                mma_commit_elect(&a_free[st]);
-                if (++st == NST) { st = 0; ph ^= 1u; }
-                // output rows whose last source row this was (at the bottom of a 'full' problem several at once)
-                const int done_to = ty == w.tb ? w.y1 : min(w.y1, ty - g.offy + 1);
-                for (; next_out < done_to; ++next_out) {
-                    mma_commit_elect(&d_full[slot_out]);
-                    if (++slot_out == RSD) slot_out = 0;
+        // The one issuing warp is also the one that keeps the books (which rows enter the window, where it wraps, which
+        // stage and which slots to wait for): ~700 clk per source row, during which the pipe ran dry (profiled: 38 % of
+        // the kernel).  The loop is therefore SOFTWARE-PIPELINED: the books and the waits of source row i + 1 are done
+        // after all but the last K step of row i have been issued - under MMAs that are executing or queued - and only
+        // then follow the last K step of row i and its commits.
+        struct Row {
+            bool valid;
+            int st, second, done;                               // operand stage, rows past the ring's wrap, rows this row completes
+            unsigned d0, bo, bo1, idesc0, idesc1, ta_hi, ta_lo;
+        };
+        long long u = blockIdx.x;
+        Unit w = make_unit(u, g, p);
+        bool in_unit = u < p.units && w.y0 < w.y1;
+        int ty = w.ta, next_in = w.y0, win_lo = w.y0, next_out = w.y0;
+        auto prep = [&]() {
+            Row r;
+            r.valid = in_unit;
+            if (!in_unit) return r;
+            const int yhi = min(w.y1 - 1, ty - g.offy + AY - 1), ylo = max(w.y0, ty - g.offy);
+            // output rows that enter the window with this source row: their slots must have been drained
+            for (; next_in <= yhi; ++next_in) {
+                if (wraps_in) TC_PROF_WAIT(dfree, mbar_wait(&d_free[slot_in], (wraps_in - 1u) & 1u));
+                if (++slot_in == RSD) { slot_in = 0; ++wraps_in; }
+            }
+            for (; win_lo < ylo; ++win_lo)
+                if (++slot_lo == RSD) slot_lo = 0;
+            TC_PROF_WAIT(afull, mbar_wait(&a_full[st], ph));
+            tc_fence_after();
+            const int cnt = yhi - ylo + 1;                      // >= 1: every source row of a unit meets one of its output rows
+            const int first = min(cnt, RSD - slot_lo);
+            r.second = cnt - first;
+            r.bo = (unsigned)((ylo + g.offy - ty) * NP);        // first row block of B: ay of the window's first row
+            r.bo1 = r.bo + (unsigned)(first * NP);
+            r.d0 = tmem_u + (unsigned)(slot_lo * NP);
+            r.idesc0 = idesc_tf32(kTile, first * NP);
+            r.idesc1 = idesc_tf32(kTile, max(r.second, 1) * NP);
+            r.ta_hi = tmem_u + (unsigned)(p.a_col0 + st * 2 * KM);
+            r.ta_lo = r.ta_hi + (unsigned)KM;
+            r.st = st;
+            if (++st == NST) { st = 0; ph ^= 1u; }
+            // output rows whose last source row this is (at the bottom of a 'full' problem several at once)
+            const int done_to = ty == w.tb ? w.y1 : min(w.y1, ty - g.offy + 1);
+            r.done = max(done_to - next_out, 0);
+            next_out += r.done;
+            // advance to the next source row (of the next segment when this one is finished)
+            if (++ty > w.tb) {
+                u += gridDim.x;
+                in_unit = u < p.units;
+                if (in_unit) {
+                    w = make_unit(u, g, p);
+                    in_unit = w.y0 < w.y1;
+                    ty = w.ta; next_in = w.y0; win_lo = w.y0; next_out = w.y0;
+                    slot_lo = slot_in;                          // the segment's first output row enters here
                 }
             }
+            return r;
+        };
+        auto issue = [&](const Row &r, int ks_a, int ks_b) {     // K steps [ks_a, ks_b) of a row (compile-time bounds when inlined)
+            if (r.second > 0) {                                 // the window wraps around the ring: two runs of slots
+#pragma unroll
+                for (int ks = 0; ks < kSteps; ++ks)
+                    if (ks >= ks_a && ks < ks_b) {
+                        const unsigned kb = r.bo + (unsigned)ks * b_step16, kb1 = r.bo1 + (unsigned)ks * b_step16;
+                        mma_tf32_ts2<true>(r.d0, r.ta_hi + 8u * ks, w_hi + kb, desc_hi, r.idesc0);
+                        mma_tf32_ts2<true>(tmem_u, r.ta_hi + 8u * ks, w_hi + kb1, desc_hi, r.idesc1);
+                        mma_tf32_ts2<true>(r.d0, r.ta_lo + 8u * ks, w_hi + kb, desc_hi, r.idesc0);
+                        mma_tf32_ts2<true>(tmem_u, r.ta_lo + 8u * ks, w_hi + kb1, desc_hi, r.idesc1);
+                        mma_tf32_ts2<true>(r.d0, r.ta_hi + 8u * ks, w_lo + kb, desc_hi, r.idesc0);
+                        mma_tf32_ts2<true>(tmem_u, r.ta_hi + 8u * ks, w_lo + kb1, desc_hi, r.idesc1);
+                    }
+            } else {
+#pragma unroll
+                for (int ks = 0; ks < kSteps; ++ks)
+                    if (ks >= ks_a && ks < ks_b) {
+                        const unsigned kb = r.bo + (unsigned)ks * b_step16;
+                        mma_tf32_ts2<true>(r.d0, r.ta_hi + 8u * ks, w_hi + kb, desc_hi, r.idesc0);
+                        mma_tf32_ts2<true>(r.d0, r.ta_lo + 8u * ks, w_hi + kb, desc_hi, r.idesc0);
+                        mma_tf32_ts2<true>(r.d0, r.ta_hi + 8u * ks, w_lo + kb, desc_hi, r.idesc0);
+                    }
+            }
+        };
+        Row cur = prep();
+        while (cur.valid) {
+#ifdef TNMF_TC_PROFILE
+            const long long t_i = clock64();
+#endif
+            if (kSteps > 1 && elect_one()) issue(cur, 0, kSteps - 1);
+            __syncwarp();
+#ifdef TNMF_TC_PROFILE
+            prof_issue += clock64() - t_i;
+#endif
+            const Row nxt = prep();
+#ifdef TNMF_TC_PROFILE
+            const long long t_j = clock64();
+#endif
+            if (elect_one()) issue(cur, kSteps > 1 ? kSteps - 1 : 0, kSteps);
+            __syncwarp();
+#ifdef TNMF_TC_PROFILE
+            prof_issue += clock64() - t_j;
+#endif
+            mma_commit_elect(&a_free[cur.st]);
+            for (int i = 0; i < cur.done; ++i) {
+                mma_commit_elect(&d_full[slot_out]);
+                if (++slot_out == RSD) slot_out = 0;
+            }
+            cur = nxt;
         }
 #ifdef TNMF_TC_PROFILE
         prof_total += clock64();
