@@ -143,3 +143,49 @@ def test_backend_refuses_to_run_without_cuda():
     from tnmf_b200 import B200_Backend
     with pytest.raises(RuntimeError):
         B200_Backend()
+
+
+def test_kernel_names_at_the_baseline_configurations(lib):
+    """Which __global__ function serves each operation of the BASELINE geometries (tnmf_kernel_name; the planning code
+    runs without a device): cfg2 and cfg3 on the tcgen05 kernels whose streamed operand lives in tensor memory, cfg4 (as
+    one image of signal rows) and cfg5 on the FP32 kernels."""
+    def names(p):
+        return [lib.tnmf_kernel_name(ctypes.byref(p), op).decode() for op in (0, 1, 2)]
+    cfg2 = _lib.make_problem(64, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32, 'valid', 'auto', 16 * 266 * 268, 266 * 268, 268)
+    assert names(cfg2) == ['recon_ts_kernel', 'hupd_ts_kernel', 'gradw_ts_kernel']
+    cfg3 = _lib.make_problem(1024, 1, 32, (128, 128), (15, 15), _lib.TNMF_F32, 'valid', 'auto', 32 * 142 * 144, 142 * 144, 144)
+    assert names(cfg3) == ['recon_os_kernel', 'hupd_ts_kernel', 'gradw_ns_kernel']
+    cfg3.flags = _lib.FLAG_NO_TMEM_OPERAND                   # the round-1 forms (operands in shared memory)
+    assert names(cfg3)[1:] == ['hupd_tc_kernel', 'gradw_tc_kernel']
+    cfg3.flags = _lib.FLAG_NO_TC
+    assert names(cfg3) == ['recon_tma_kernel', 'hupd_tma_kernel', 'gradw_tma_kernel']
+    cfg4 = _lib.make_problem(2048, 1, 64, (4096,), (128,), _lib.TNMF_F32, 'valid', 'auto', 64 * 4224, 4224)
+    assert names(cfg4) == ['recon_tma_kernel', 'hupd_tma_kernel', 'gradw_tma_kernel']
+    cfg5 = _lib.make_problem(16, 1, 8, (512, 512), (64, 64), _lib.TNMF_F32, 'valid', 'auto', 8 * 575 * 576, 575 * 576, 576)
+    assert names(cfg5) == ['recon_tma_kernel', 'tiled::hupd_kernel', 'gradw_tma_kernel']
+    f64 = _lib.make_problem(4, 2, 3, (20, 17), (5, 3), _lib.TNMF_F64)
+    assert names(f64) == ['generic_reconstruct_kernel', 'generic_gradient_h_kernel', 'generic_gradient_w_kernel']
+    cfg2.reserved = 1
+    assert names(cfg2) == ['none'] * 3
+
+
+def test_peer_world_layout_and_buffer_size(lib):
+    """struct tnmf_peer_world (include/tnmf_b200.h) and the size of the NVLink exchange buffer of
+    tnmf_allreduce_update_w: data[2 parities][world][2 * count] + flags[world][atoms x channels]."""
+    assert ctypes.sizeof(_lib.PeerWorld) == 8 + _lib.MAX_PEERS * ctypes.sizeof(ctypes.c_void_p)
+    assert _lib.PeerWorld.buffers.offset == 8
+    header = open(os.path.join(os.path.dirname(__file__), '..', 'include', 'tnmf_b200.h')).read()
+    assert f'#define TNMF_MAX_PEERS {_lib.MAX_PEERS}' in header
+    p = _lib.make_problem(0, 3, 16, (256, 256), (11, 11), _lib.TNMF_F32)
+    count = 16 * 3 * 121
+    for world in (1, 2, 8, 16):
+        data = 2 * world * 2 * count * 4
+        assert lib.tnmf_peer_buffer_bytes(ctypes.byref(p), world) == (data + 127) // 128 * 128 + world * 16 * 3 * 4
+    assert lib.tnmf_peer_buffer_bytes(ctypes.byref(p), 17) == 0
+    assert lib.tnmf_peer_buffer_bytes(ctypes.byref(p), 0) == 0
+    # argument validation happens before anything is launched
+    pw = _lib.PeerWorld()
+    pw.world, pw.rank = 2, 0
+    assert lib.tnmf_allreduce_update_w(ctypes.byref(p), 1, 1, ctypes.byref(pw), 1, 1e-9, None) == _lib.TNMF_EINVAL   # no buffers
+    pw.world, pw.rank = 2, 2
+    assert lib.tnmf_allreduce_update_w(ctypes.byref(p), 1, 1, ctypes.byref(pw), 1, 1e-9, None) == _lib.TNMF_EINVAL
