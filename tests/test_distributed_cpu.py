@@ -117,20 +117,23 @@ def test_two_gloo_ranks_equal_one_process(batch_size):
 class OracleOps:
     """The CPU oracle as the arithmetic provider of RowShardedNMF (what B200Ops is on the GPU box)."""
 
+    def __init__(self, mode='valid'):
+        self.mode = mode
+
     def setup(self, V_local, atom_shape, n_atoms, W0, H0):
         self.V = np.array(V_local, dtype=np.float64)
         return torch.from_numpy(np.array(W0, dtype=np.float64)), torch.from_numpy(np.array(H0, dtype=np.float64))
 
     def update_H(self, W, H, sparsity, eps):
-        neg, pos = orc.reconstruction_gradient_H(self.V, W.numpy(), H.numpy())
+        neg, pos = orc.reconstruction_gradient_H(self.V, W.numpy(), H.numpy(), self.mode)
         orc.multiplicative_update(H.numpy(), neg, pos, sparsity)
 
     def gradient_W(self, W, H, own):
         Hn, Wn = H.numpy(), W.numpy()
-        R = orc.reconstruct(Wn, Hn)
+        R = orc.reconstruct(Wn, Hn, self.mode)
         H_own = np.zeros_like(Hn)
         H_own[:, :, own[0]:own[1]] = Hn[:, :, own[0]:own[1]]
-        Hp = orc.pad_activations(H_own, Wn.shape[2:], 'valid')
+        Hp = orc.pad_activations(H_own, Wn.shape[2:], self.mode)
         return torch.from_numpy(np.stack([orc._correlate_with_activations(self.V, Hp, Wn.shape[2:]),
                                           orc._correlate_with_activations(R, Hp, Wn.shape[2:])]))
 
@@ -139,19 +142,19 @@ class OracleOps:
         orc.multiplicative_update(W.numpy(), g[0].copy(), g[1].copy(), normalization_axes=tuple(range(2, W.dim())))
 
     def energy_rows(self, W, H, rows):
-        R = orc.reconstruct(W.numpy(), H.numpy())
+        R = orc.reconstruct(W.numpy(), H.numpy(), self.mode)
         d = self.V[:, :, rows[0]:rows[1]] - R[:, :, rows[0]:rows[1]]
         return torch.tensor(0.5 * np.sum(d * d))
 
 
-def _halo_rank_main(rank, world, port, V, atoms, atom_shape, iters, sparsity, seeds, out):
+def _halo_rank_main(rank, world, port, V, atoms, atom_shape, iters, sparsity, seeds, out, mode='valid'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         from tnmf_b200.halo import RowShardedNMF
         np.random.seed(seeds[rank])
-        nmf = RowShardedNMF(atoms, atom_shape, ops=OracleOps())
+        nmf = RowShardedNMF(atoms, atom_shape, ops=OracleOps(mode), reconstruction_mode=mode)
         energies = []
         nmf.fit(V, n_iterations=iters, sparsity_H=sparsity,
                 progress_callback=lambda m, i: energies.append(m.energy()) or True)
@@ -163,25 +166,32 @@ def _halo_rank_main(rank, world, port, V, atoms, atom_shape, iters, sparsity, se
 
 def test_row_plan_bands_and_halos():
     from tnmf_b200.halo import row_plan
-    for d, a, world in ((24, 5, 2), (24, 5, 3), (40, 1, 4), (17, 4, 2), (9, 9, 2)):
-        p, t = a - 1, d + a - 1
-        plans = [row_plan(t, d, p, world, r) for r in range(world)]
-        assert plans[0]['t0'] == 0 and plans[-1]['t1'] == t
-        assert all(x['t1'] == y['t0'] for x, y in zip(plans, plans[1:]))
-        for r, pl in enumerate(plans):
-            assert pl['lower'][1] - pl['lower'][0] == (p if r else 0)                   # p halo rows from below ...
-            assert pl['upper'][1] - pl['upper'][0] == (p if r < world - 1 else 0)       # ... and from above
-            assert pl['upper'][1] == pl['y1'] + p - pl['y0']                            # the local 'valid' problem's T
-        # the energy rows partition the sample rows
-        e = [(pl['e_rows'][0] + pl['y0'], pl['e_rows'][1] + pl['y0']) for pl in plans]
-        assert e[0][0] == 0 and e[-1][1] == d and all(x[1] == y[0] for x, y in zip(e, e[1:]))
+    for mode in ('valid', 'full'):
+        for d, a, world in ((24, 5, 2), (24, 5, 3), (40, 1, 4), (17, 4, 2), (27, 9, 2)):
+            p = a - 1
+            t = d + p if mode == 'valid' else d - p
+            plans = [row_plan(t, d, p, world, r, mode) for r in range(world)]
+            assert plans[0]['t0'] == 0 and plans[-1]['t1'] == t
+            assert all(x['t1'] == y['t0'] for x, y in zip(plans, plans[1:]))
+            for r, pl in enumerate(plans):
+                assert pl['lower'][1] - pl['lower'][0] == (p if r else 0)                   # p halo rows from below ...
+                assert pl['upper'][1] - pl['upper'][0] == (p if r < world - 1 else 0)       # ... and from above
+                # the local problem is an ordinary problem of the same mode: T_local = D_local +- p
+                assert pl['upper'][1] == (pl['v1'] - pl['v0']) + (p if mode == 'valid' else -p)
+                assert 0 <= pl['v0'] < pl['v1'] <= d
+            # the energy rows partition the sample rows
+            e = [(pl['e_rows'][0] + pl['v0'], pl['e_rows'][1] + pl['v0']) for pl in plans]
+            assert e[0][0] == 0 and e[-1][1] == d and all(x[1] == y[0] for x, y in zip(e, e[1:]))
     with pytest.raises(ValueError):
         row_plan(12, 8, 4, 4, 0)            # bands of 3 rows, halo of 4
+    with pytest.raises(NotImplementedError):
+        row_plan(8, 8, 4, 2, 0, 'circular')
 
 
+@pytest.mark.parametrize('mode', ['valid', 'full'])
 @pytest.mark.parametrize('world,shape,atom_shape', [(2, (3, 2, 24, 10), (5, 4)), (3, (2, 1, 30, 7), (4, 3)),
                                                     (2, (4, 2, 40), (6,))])
-def test_row_sharded_fit_equals_single_process(world, shape, atom_shape):
+def test_row_sharded_fit_equals_single_process(world, shape, atom_shape, mode):
     """Bands of activation rows + halo exchange + masked W gradient == the single-process fit (float64: identical up to
     summation order), from one seeded start; ranks 1.. seed differently on purpose (W is broadcast from rank 0, and every
     rank's band must come from rank 0's draw for the comparison - so H seeds are equal, W seeds are not needed)."""
@@ -189,14 +199,14 @@ def test_row_sharded_fit_equals_single_process(world, shape, atom_shape):
     V = rng.random(shape)
     iters, sparsity, atoms = 8, 0.05, 3
     np.random.seed(31)
-    ref = orc.OracleNMF(n_atoms=atoms, atom_shape=atom_shape)
+    ref = orc.OracleNMF(n_atoms=atoms, atom_shape=atom_shape, reconstruction_mode=mode)
     e_ref = []
     ref.fit_batch(V, n_iterations=iters, sparsity_H=sparsity,
                   progress_callback=lambda m, i: e_ref.append(float(m.energy())) or True)
     ctx = mp.get_context('spawn')
     with ctx.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_halo_rank_main, args=(world, _free_port(), V, atoms, atom_shape, iters, sparsity, [31] * world, out),
+        mp.spawn(_halo_rank_main, args=(world, _free_port(), V, atoms, atom_shape, iters, sparsity, [31] * world, out, mode),
                  nprocs=world, join=True)
         results = [out[r] for r in range(world)]
     W0, H0, e0, _, exchanges = results[0]

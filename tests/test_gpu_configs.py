@@ -167,7 +167,7 @@ def test_two_ranks_unseeded_start_from_one_dictionary():
 # ---------------------------------------------------------------------------------------------------------
 # spatial (halo) sharding with the real kernels: bands of activation rows on two ranks
 # ---------------------------------------------------------------------------------------------------------
-def _halo_rank_main(rank, world, port, V, atoms, atom_shape, kw_fit, out):
+def _halo_rank_main(rank, world, port, V, atoms, atom_shape, kw_fit, out, mode='valid'):
     import torch.distributed as dist
     from tnmf_b200 import RowShardedNMF
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -176,7 +176,7 @@ def _halo_rank_main(rank, world, port, V, atoms, atom_shape, kw_fit, out):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         np.random.seed(41)
-        nmf = RowShardedNMF(atoms, atom_shape)
+        nmf = RowShardedNMF(atoms, atom_shape, reconstruction_mode=mode)
         energies = []
         nmf.fit(V, progress_callback=lambda m, i: energies.append(m.energy()) or True, **kw_fit)
         H = nmf.gather_H()
@@ -185,7 +185,7 @@ def _halo_rank_main(rank, world, port, V, atoms, atom_shape, kw_fit, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize('case', ['f64', 'f32_tc'])
+@pytest.mark.parametrize('case', ['f64', 'f64_full', 'f32_tc'])
 def test_row_sharded_fit_equals_single_gpu_and_oracle(case):
     """tnmf_b200.RowShardedNMF on two ranks (bands of activation rows, halo exchange every half iteration, W gradient of
     the owned rows only, summed over the ranks) == the single-process oracle, with the CUDA kernels doing the arithmetic:
@@ -193,7 +193,8 @@ def test_row_sharded_fit_equals_single_gpu_and_oracle(case):
     north_star tolerances."""
     import torch.multiprocessing as mp
     rng = np.random.default_rng(8)
-    if case == 'f64':
+    mode = 'full' if case.endswith('full') else 'valid'
+    if case.startswith('f64'):
         V, atoms, atom_shape, iters = rng.random((3, 2, 24, 20)), 5, (5, 4), 10
         rtol_e, tol = 1e-9, 1e-9
     else:
@@ -201,14 +202,15 @@ def test_row_sharded_fit_equals_single_gpu_and_oracle(case):
         rtol_e, tol = 1e-4, 1e-3
     kw_fit = dict(n_iterations=iters, sparsity_H=0.05)
     np.random.seed(41)
-    ref = orc.OracleNMF_FFT(n_atoms=atoms, atom_shape=atom_shape) if case != 'f64' else orc.OracleNMF(atoms, atom_shape)
+    ref = (orc.OracleNMF_FFT(n_atoms=atoms, atom_shape=atom_shape) if case == 'f32_tc'
+           else orc.OracleNMF(atoms, atom_shape, reconstruction_mode=mode))
     e_ref = []
     ref.fit_batch(V.astype(np.float64), progress_callback=lambda m, i: e_ref.append(float(m.energy())) or True, **kw_fit)
     world = 2
     ctx = mp.get_context('spawn')
     with ctx.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_halo_rank_main, args=(world, _free_port(), V, atoms, atom_shape, kw_fit, out), nprocs=world, join=True)
+        mp.spawn(_halo_rank_main, args=(world, _free_port(), V, atoms, atom_shape, kw_fit, out, mode), nprocs=world, join=True)
         results = [out[r] for r in range(world)]
     W0, H0, e0, names = results[0]
     print(case, names, 'energy', e0[-1], e_ref[-1])

@@ -2,7 +2,8 @@
 Spatial (halo) sharding: ONE problem whose samples are too large - or too few - to shard over samples is cut along
 the first shift axis ("rows") and every rank owns a band of activation rows.
 
-Default mode only ('valid', tnmf/backends/_Backend.py:60-73: T = D + A - 1, p = A_y - 1).  Globally
+Derivation for the default mode ('valid', tnmf/backends/_Backend.py:60-73: T = D + A - 1, p = A_y - 1; 'full' is the mirror
+image with the halos on the sample side, see `row_plan`).  Globally
     R[y]    = sum_ay W[ay] * H[y + p - ay]            R row y needs the activation rows [y, y + p]
     negH[t] = sum_ay W[ay] * V[t - p + ay]            activation row t needs the sample rows [t - p, t]
     negW[ay] = sum_t H[t] * V[t - p + ay]             a plain sum over activation rows
@@ -28,17 +29,32 @@ import torch.distributed as dist
 from .distributed import shard_bounds
 
 
-def row_plan(t_rows: int, d_rows: int, p: int, world: int, rank: int) -> dict:
-    """Bands of the `t_rows` = d_rows + p activation rows: owned rows [t0, t1), local sample rows [y0, y1), and where the
-    owned band and the two halos sit inside the local activation tensor (rows [y0, y1 + p) of the global one)."""
-    if t_rows != d_rows + p:
-        raise ValueError("halo sharding is defined for the 'valid' mode (T = D + A - 1)")
+def row_plan(t_rows: int, d_rows: int, p: int, world: int, rank: int, mode: str = 'valid') -> dict:
+    """Bands of the activation rows: owned rows [t0, t1) of the global tensor, the sample rows [v0, v1) of the band's local
+    problem, the global row h0 of the first LOCAL activation row, and - in local activation rows - where the owned band
+    (`own`) and the halos (`lower`, `upper`) sit; `e_rows` = the local sample rows whose energy this rank adds up.
+
+    'valid' (T = D + p): local problem = sample rows [max(0, t0 - p), min(D, t1)), activation rows from the same row on.
+    'full'  (T = D - p, R[y] needs the activation rows [y - p, y], activation row t the sample rows [t, t + p]): the owned
+    band needs R on [t0, t1 + p), which needs the activation rows [t0 - p, t1 + p): local activation rows
+    [h0, h1) = [max(0, t0 - p), min(T, t1 + p)), local sample rows [h0, h1 + p)."""
+    if mode not in ('valid', 'full'):
+        raise NotImplementedError(f"halo sharding is not defined for reconstruction mode '{mode}'")
+    if t_rows != (d_rows + p if mode == 'valid' else d_rows - p):
+        raise ValueError('activation and sample extents do not belong to this mode')
     if world > 1 and t_rows // world < max(p, 1):
         raise ValueError(f'{world} ranks leave bands of {t_rows // world} rows, thinner than the halo of {p} rows')
     t0, t1 = shard_bounds(t_rows, world, rank)
-    y0, y1 = max(0, t0 - p), min(d_rows, t1)
-    return dict(t0=t0, t1=t1, y0=y0, y1=y1, own=(t0 - y0, t1 - y0), lower=(0, t0 - y0), upper=(t1 - y0, y1 + p - y0),
-                e_rows=(min(d_rows, t0) - y0 if rank else 0, y1 - y0))
+    if mode == 'valid':
+        v0, v1 = max(0, t0 - p), min(d_rows, t1)
+        h0, h1 = v0, v1 + p
+        e0, e1 = (min(d_rows, t0) if rank else 0), v1
+    else:
+        h0, h1 = max(0, t0 - p), min(t_rows, t1 + p)
+        v0, v1 = h0, h1 + p
+        e0, e1 = t0, (t1 if rank < world - 1 else d_rows)
+    return dict(t0=t0, t1=t1, v0=v0, v1=v1, h0=h0, own=(t0 - h0, t1 - h0), lower=(0, t0 - h0), upper=(t1 - h0, h1 - h0),
+                e_rows=(e0 - v0, e1 - v0))
 
 
 class RowSharding:
@@ -99,9 +115,9 @@ class RowSharding:
 class B200Ops:
     """The arithmetic of one band on the CUDA kernels (B200_Backend on the band's local 'valid' problem)."""
 
-    def __init__(self, **backend_kwargs):
+    def __init__(self, reconstruction_mode: str = 'valid', **backend_kwargs):
         from .backend import B200_Backend
-        self.be = B200_Backend(reconstruction_mode='valid', **backend_kwargs)
+        self.be = B200_Backend(reconstruction_mode=reconstruction_mode, **backend_kwargs)
         self.V = None
 
     def setup(self, V_local, atom_shape, n_atoms, W0, H0):
@@ -141,15 +157,19 @@ class RowShardedNMF:
     Batch multiplicative updates (tnmf/TransformInvariantNMF.py:282-348) with the activation rows sharded over the ranks.
 
     Every rank passes the same global V (only its band of sample rows is kept on the device).  `W` is identical on all
-    ranks, `H` is the rank's band of activation rows [t0, t1).  Supported: 'valid' mode, sparsity; the inhibition terms
+    ranks, `H` is the rank's band of activation rows [t0, t1).  Supported: 'valid' and 'full' modes, sparsity; the inhibition terms
     convolve H along the sharded axis and are not offered here.
     """
 
-    def __init__(self, n_atoms: int, atom_shape: Tuple[int, ...], process_group=None, ops=None, **backend_kwargs):
+    def __init__(self, n_atoms: int, atom_shape: Tuple[int, ...], process_group=None, ops=None,
+                 reconstruction_mode: str = 'valid', **backend_kwargs):
         self.n_atoms, self.atom_shape = int(n_atoms), tuple(int(a) for a in atom_shape)
+        self.mode = reconstruction_mode
+        if self.mode not in ('valid', 'full'):
+            raise NotImplementedError(f"halo sharding is not defined for reconstruction mode '{self.mode}'")
         self.eps = 1.e-9
         self.sharding = RowSharding(process_group)
-        self.ops = ops if ops is not None else B200Ops(**backend_kwargs)
+        self.ops = ops if ops is not None else B200Ops(reconstruction_mode=self.mode, **backend_kwargs)
         self.plan = None
         self._W = self._H = None
 
@@ -158,8 +178,9 @@ class RowShardedNMF:
         draws cast to V.dtype): every rank draws the full tensors and keeps its band."""
         V = np.asarray(V)
         sh, p = self.sharding, self.atom_shape[0] - 1
-        t_shape = tuple(d + a - 1 for d, a in zip(V.shape[2:], self.atom_shape))
-        self.plan = row_plan(t_shape[0], V.shape[2], p, sh.world, sh.rank)
+        sign = 1 if self.mode == 'valid' else -1
+        t_shape = tuple(d + sign * (a - 1) for d, a in zip(V.shape[2:], self.atom_shape))
+        self.plan = row_plan(t_shape[0], V.shape[2], p, sh.world, sh.rank, self.mode)
         H0 = np.asarray(1 - np.random.rand(V.shape[0], self.n_atoms, *t_shape), dtype=V.dtype)
         W0 = np.asarray(1 - np.random.rand(self.n_atoms, V.shape[1], *self.atom_shape), dtype=V.dtype)
         W0 /= W0.sum(axis=tuple(range(2, W0.ndim)), keepdims=True)
@@ -168,8 +189,8 @@ class RowShardedNMF:
             dist.broadcast_object_list(box, src=sh._peer(0), group=sh.group)      # pylint: disable=protected-access
             W0 = box[0]
         pl = self.plan
-        V_local = np.ascontiguousarray(V[:, :, pl['y0']:pl['y1']])
-        H_local = np.ascontiguousarray(H0[:, :, pl['y0']:pl['y1'] + p])
+        V_local = np.ascontiguousarray(V[:, :, pl['v0']:pl['v1']])
+        H_local = np.ascontiguousarray(H0[:, :, pl['h0']:pl['h0'] + pl['upper'][1]])
         self._W, self._H = self.ops.setup(V_local, self.atom_shape, self.n_atoms, W0, H_local)
 
     def step(self, sparsity: float = 0.) -> None:
